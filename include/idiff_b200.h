@@ -1,0 +1,160 @@
+/*
+ * idiff_b200.h -- C ABI of libidiff_b200.so: the sm_100a (B200) kernels behind the
+ * InstanceDiffusion sampling hot path.
+ *
+ * The reference (frank-xwang/InstanceDiffusion) is pure Python/PyTorch and has no FFI; its
+ * seam is the set of nn.Module classes resolved by dotted path (ldm/util.py:71-84).  Each entry
+ * point below replaces the arithmetic of one (group of) reference call site(s); the Python
+ * mirror modules in instancediffusion_b200/ldm/... call these through ctypes with raw device
+ * pointers (tensor.data_ptr()) and the current CUDA stream.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; idiff_last_error() gives the text.
+ *   - nothing here allocates device memory or synchronises; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*).  Buffers are caller-owned.
+ *   - activations are fp16, token-major / NHWC: a (B,H,W,C) image is the (B*H*W, C) row-major
+ *     matrix the transformer blocks see, so the reference's NCHW<->(B,HW,C) rearranges vanish.
+ *   - weights are fp16 [out_features, in_features] row-major (conv3x3: [Cout, 3, 3, Cin]).
+ */
+#ifndef IDIFF_B200_H
+#define IDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* idiff_last_error(void);
+int idiff_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * idiff_gemm: out = epilogue(A . W^T) on tcgen05 tensor cores (TMA-staged 128B-swizzled tiles,
+ * fp32 accumulation in TMEM).  Replaces every nn.Linear / 1x1 conv / 3x3 conv of the path:
+ *   attention.py:41 (GEGLU proj), :62 (FF out), :121-125,175-179 (to_q/k/v/to_out), :297 (fuser
+ *   linear), :354,363 (proj_in/proj_out 1x1); openaimodel.py:186,213 (ResBlock conv3x3), :109
+ *   (Upsample conv), :134 (Downsample conv), :205 (emb_layers), :361-363 (time_embed), :464 (out);
+ *   text_grounding_net.py:75-81 (UniFusion MLPs).
+ * conv3x3 (conv_h > 0): A is the NHWC activation (conv_b, conv_h, conv_w, conv_cin), gathered
+ * tap by tap with 4-D TMA boxes and hardware zero fill at the borders (no im2col buffer);
+ * W is [N, 9*conv_cin] with k = (ky*3+kx)*conv_cin + c; stride 1, padding 1.
+ * ------------------------------------------------------------------------------------------- */
+#define IDIFF_EPI_GEGLU 1       /* W rows interleaved per 64: [value(64) | gate(64)]; out has N/2 cols:
+                                   (value+b)*gelu_erf(gate+b)            (attention.py:41-43)   */
+#define IDIFF_EPI_SILU 2        /* x -> x*sigmoid(x) after bias                                   */
+#define IDIFF_OUT_F32_NCHW 4    /* out is fp32 (B, N, H*W): the eps layout the samplers consume   */
+
+typedef struct {
+  const void* a;        /* fp16 [M, K] (lda)            | conv: fp16 NHWC activation            */
+  const void* w;        /* fp16 [N, K] (ldw)                                                    */
+  void* out;            /* fp16 [M, N or N/2] (ldo)     | fp32 NCHW with IDIFF_OUT_F32_NCHW      */
+  const float* bias;    /* [N] or NULL                                                          */
+  const void* rowadd;   /* fp16 [M / rows_per_batch, N] added per batch (ResBlock emb) or NULL  */
+  const void* residual; /* fp16 [M, N_out] (ldr) or NULL: out = residual + gate * (...)         */
+  float gate;           /* scale * tanh(alpha) of GatedSelfAttentionDense; 1 for plain residual */
+  int M, N, K;
+  int lda, ldw, ldo, ldr;
+  int rows_per_batch;
+  int flags;
+  int conv_b, conv_h, conv_w, conv_cin;
+} idiff_gemm_args;
+int idiff_gemm(const idiff_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * idiff_attention: softmax(Q K^T * scale) V per (batch, head), flash-style online softmax with
+ * S/O accumulators in TMEM.  Keys/values come from up to two segments: segment 0 = the visual
+ * tokens (or the 77 text tokens), segment 1 = the 184 UniFusion object tokens of
+ * GatedSelfAttentionDense (attention.py:304-309) -- queries exist only for the visual rows, which
+ * is exactly the slice the reference keeps (:308).  Replaces F.scaled_dot_product_attention at
+ * attention.py:134-144 (cross), :257-267 (self / gated-self).
+ * Each operand is fp16 with row stride *_ld elements; head h occupies columns [h*d, (h+1)*d)
+ * from the given pointer; batch b starts at row b*rows (rows = nq / n0 / n1).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void *q, *k0, *v0, *k1, *v1;
+  void* out; /* fp16 [batch*nq, heads*head_dim] (out_ld) */
+  int q_ld, k0_ld, v0_ld, k1_ld, v1_ld, out_ld;
+  int batch, heads, head_dim; /* head_dim in {40, 80, 160} */
+  int nq, n0, n1;             /* n1 may be 0 */
+  int kv1_batch;              /* 1: segment 1 shared by all batch entries; else == batch */
+  float scale;                /* head_dim^-0.5 (attention.py:102,164) */
+} idiff_attn_args;
+int idiff_attention(const idiff_attn_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Normalisation (HBM-bound passes)
+ *   idiff_groupnorm: GroupNorm32 (util.py:223-225, eps 1e-5) / Normalize (attention.py:75-76,
+ *   eps 1e-6) over NHWC fp16, statistics in fp32, optional fused SiLU (openaimodel.py:184,208).
+ *   stats_ws: B*groups*2 floats of scratch (zeroed by the call).
+ *   idiff_layernorm: nn.LayerNorm(C) (attention.py:294-295,320-322), one warp per row.
+ * ------------------------------------------------------------------------------------------- */
+int idiff_groupnorm(const void* x, void* y, const float* gamma, const float* beta, float* stats_ws,
+                    int batch, int hw, int channels, int groups, float eps, int fuse_silu,
+                    void* stream);
+int idiff_layernorm(const void* x, void* y, const float* gamma, const float* beta, int rows,
+                    int channels, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * idiff_scaleu_concat: ScaleU skip-connection rescale (openaimodel.py:519-539):
+ *   out[..., :C1]      = h * (tanh(b_c) + 1)
+ *   out[..., C1:C1+C2] = Fourier_filter(skip, threshold=1, scale=s) = skip + (s-1) * P_low(skip)
+ * with P_low the real part of the inverse DFT restricted to bins {-1,0}x{-1,0} (7 real
+ * reductions per (b,c) plane; closed form of openaimodel.py:25-48).  coef_ws: B*C2*8 floats.
+ * b1: per-channel factor tanh(b)+1 (C1 floats, device); s: tanh(scaleu_s)+1 (host scalar).
+ * ------------------------------------------------------------------------------------------- */
+int idiff_scaleu_concat(const void* h, const void* skip, void* out, const float* b1, float s,
+                        float* coef_ws, int batch, int height, int width, int c1, int c2,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout / resampling helpers
+ * ------------------------------------------------------------------------------------------- */
+/* fp32 NCHW (B,C,H,W) -> fp16 NHWC with channels zero-padded to c_pad */
+int idiff_nchw_f32_to_nhwc_f16(const float* x, void* y, int batch, int c, int hw, int c_pad,
+                               void* stream);
+/* fp16 NHWC -> fp32 NCHW */
+int idiff_nhwc_f16_to_nchw_f32(const void* x, float* y, int batch, int c, int hw, void* stream);
+/* F.interpolate(scale_factor=2, mode="nearest") on NHWC fp16 (openaimodel.py:107) */
+int idiff_upsample_nearest2x(const void* x, void* y, int batch, int h, int w, int c, void* stream);
+/* im2col for the stride-2 padding-1 3x3 Downsample conv (openaimodel.py:130-134):
+   out [B*(H/2)*(W/2), 9*C], k = (ky*3+kx)*C + c */
+int idiff_im2col_s2(const void* x, void* y, int batch, int h, int w, int c, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * idiff_fourier_embed: UniFusion instance-token builder front end
+ * (text_grounding_net.py:216-225,248-276 + util.py:12-26): for every (b, slot) row writes
+ *   out[row, :text_dim]            = text*m + (1-m)*null_text            (if text != NULL)
+ *   out[row, text_dim + k*2D + j]     = sin(f_k * x_j)*m' + (1-m')*null_pos[...]
+ *   out[row, text_dim + k*2D + D + j] = cos(f_k * x_j)*m' + (1-m')*null_pos[...]
+ * f_k = 100^(k/16), k < 16.  m = masks[row]; m' = 0 if dropped, else masks[row] (mask_mode 0)
+ * or ((sum_j x_j + masks[row]) > 0) (mask_mode 1: scribbles / polygons, :267,272).
+ * ------------------------------------------------------------------------------------------- */
+int idiff_fourier_embed(const float* coords, const float* masks, const float* text,
+                        const float* null_text, const float* null_pos, void* out, int rows,
+                        int coord_dim, int text_dim, int out_ld, int mask_mode, int dropped,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * idiff_plms_update: fused sampler epilogue (plms.py:121-165 / plms_instance.py:166-210):
+ *   e   = e_u + gs*(e_c - e_u)            (CFG; e_u may be NULL -> e = e_c)
+ *   e'  = c0*e + c1*old1 + c2*old2 + c3*old3   (Adams-Bashforth weights chosen by the host;
+ *         for the first-step Euler predictor pass c0=1; for the corrector e' = (e_prev + e)/2
+ *         is expressed with old1)
+ *   x_prev = sqrt(a_prev)*(x - sqrt(1-a_t)*e')/sqrt(a_t) + sqrt(1-a_prev)*e'
+ * All fp32, n elements.  e_out receives the post-CFG e (history), x_out the new latent.
+ * ------------------------------------------------------------------------------------------- */
+int idiff_plms_update(const float* x, const float* e_c, const float* e_u, float gs,
+                      const float* old1, const float* old2, const float* old3, float c0, float c1,
+                      float c2, float c3, float a_t, float a_prev, float sqrt_one_minus_at,
+                      float* e_out, float* x_out, long n, void* stream);
+/* out = mean over `count` latents given as an array of device pointers (plms_instance.py:135) */
+int idiff_latent_mean(const float* const* xs_dev, int count, float* out, long n, void* stream);
+
+/* timestep_embedding (util.py:160-180): out fp16 [B, dim] = [cos(t*f) | sin(t*f)],
+   f_k = exp(-ln(1e4)*k/(dim/2)) */
+int idiff_timestep_embedding(const float* t, void* out, int batch, int dim, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDIFF_B200_H */

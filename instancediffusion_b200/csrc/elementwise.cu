@@ -1,0 +1,401 @@
+// HBM-bound helpers of the sampling hot path: ScaleU (closed-form Fourier filter), layout
+// conversion, nearest-2x upsample, stride-2 im2col, UniFusion Fourier embedder, timestep
+// embedding and the fused PLMS sampler update.  Reference citations are at each kernel.
+#include "../../include/idiff_b200.h"
+#include "common.cuh"
+#include "host.cuh"
+
+namespace idiff {
+
+constexpr float kTwoPi = 6.283185307179586f;
+
+// ---------------------------------------------------------------------------------------------
+// ScaleU (openaimodel.py:519-539) with Fourier_filter (:25-48) in closed form:
+//   filter(x) = x + (s-1) * P_low(x),  P_low = Re IDFT of the bins (fy,fx) in {-1,0}^2
+// Per (b,c) plane seven real sums are needed:
+//   S0=sum x, Ac=sum x cos(tx), As=sum x sin(tx), Bc=sum x cos(py), Bs=sum x sin(py),
+//   Cc=sum x cos(tx+py), Cs=sum x sin(tx+py),   tx=2*pi*x/W, py=2*pi*y/H
+// and P_low(y,x) = (S0 + Ac cos tx + As sin tx + Bc cos py + Bs sin py
+//                   + Cc cos(tx+py) + Cs sin(tx+py)) / (H*W).
+// ---------------------------------------------------------------------------------------------
+constexpr int SU_THREADS = 256;
+
+__global__ void __launch_bounds__(SU_THREADS)
+scaleu_coef_kernel(const __half2* __restrict__ skip, float* __restrict__ coef, int H, int W, int C,
+                   int pix_per_block) {
+  __shared__ float tab[4 * 128];  // cos tx, sin tx, cos py, sin py
+  float* ctx = tab;
+  float* stx = tab + 128;
+  float* cpy = tab + 256;
+  float* spy = tab + 384;
+  for (int i = threadIdx.x; i < W; i += SU_THREADS) sincosf(kTwoPi * i / W, &stx[i], &ctx[i]);
+  for (int i = threadIdx.x; i < H; i += SU_THREADS) sincosf(kTwoPi * i / H, &spy[i], &cpy[i]);
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int hw = H * W;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(hw, p0 + pix_per_block);
+  const int CP = C >> 1;
+  const __half2* xb = skip + (long)b * hw * CP;
+  for (int cp = threadIdx.x; cp < CP; cp += SU_THREADS) {
+    float a0[7], a1[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) a0[k] = a1[k] = 0.f;
+    for (int pix = p0; pix < p1; ++pix) {
+      const int yy = pix / W, xx = pix - yy * W;
+      const float cx = ctx[xx], sx = stx[xx], cy = cpy[yy], sy = spy[yy];
+      const float cxy = cx * cy - sx * sy, sxy = sx * cy + cx * sy;
+      const float2 v = __half22float2(xb[(long)pix * CP + cp]);
+      const float wgt[7] = {1.f, cx, sx, cy, sy, cxy, sxy};
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        a0[k] += v.x * wgt[k];
+        a1[k] += v.y * wgt[k];
+      }
+    }
+    float* dst = coef + ((long)b * C + 2 * cp) * 8;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      atomicAdd(dst + k, a0[k]);
+      atomicAdd(dst + 8 + k, a1[k]);
+    }
+  }
+}
+
+// one thread per 8 output channels; out is (B, HW, C1+C2)
+__global__ void __launch_bounds__(SU_THREADS)
+scaleu_apply_kernel(const uint4* __restrict__ h, const uint4* __restrict__ skip, uint4* __restrict__ out,
+                    const float* __restrict__ b1, const float* __restrict__ coef, float s_minus_1,
+                    int B, int H, int W, int C1, int C2) {
+  const int CV1 = C1 >> 3, CV2 = C2 >> 3, CVO = CV1 + CV2;
+  const long total = (long)B * H * W * CVO;
+  const float inv_hw = 1.0f / (float)(H * W);
+  for (long i = (long)blockIdx.x * SU_THREADS + threadIdx.x; i < total; i += (long)gridDim.x * SU_THREADS) {
+    const int cv = (int)(i % CVO);
+    const long bp = i / CVO;  // b*HW + pix
+    uint32_t o[4];
+    if (cv < CV1) {
+      const uint4 v = h[bp * CV1 + cv];
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_half2(u[j]);
+        const int c = cv * 8 + 2 * j;
+        o[j] = pack_half2(f.x * __ldg(b1 + c), f.y * __ldg(b1 + c + 1));
+      }
+    } else {
+      const int cv2 = cv - CV1;
+      const int b = (int)(bp / (H * W));
+      const int pix = (int)(bp - (long)b * H * W);
+      const int yy = pix / W, xx = pix - yy * W;
+      float sx, cx, sy, cy;
+      sincosf(kTwoPi * xx / W, &sx, &cx);
+      sincosf(kTwoPi * yy / H, &sy, &cy);
+      const float cxy = cx * cy - sx * sy, sxy = sx * cy + cx * sy;
+      const uint4 v = skip[bp * CV2 + cv2];
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_half2(u[j]);
+        r[2 * j] = f.x;
+        r[2 * j + 1] = f.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float* cf = coef + ((long)b * C2 + cv2 * 8 + j) * 8;
+        const float4 c0 = *reinterpret_cast<const float4*>(cf);
+        const float4 c1 = *reinterpret_cast<const float4*>(cf + 4);
+        const float plow = (c0.x + c0.y * cx + c0.z * sx + c0.w * cy + c1.x * sy + c1.y * cxy + c1.z * sxy) * inv_hw;
+        r[j] += s_minus_1 * plow;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = pack_half2(r[2 * j], r[2 * j + 1]);
+    }
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout conversion
+// ---------------------------------------------------------------------------------------------
+__global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int B,
+                                            int C, int HW, int CP) {
+  const long total = (long)B * HW * CP;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CP);
+    const long bp = i / CP;
+    const int b = (int)(bp / HW);
+    const int pix = (int)(bp - (long)b * HW);
+    y[i] = (c < C) ? __float2half(x[((long)b * C + c) * HW + pix]) : __float2half(0.f);
+  }
+}
+__global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ x, float* __restrict__ y, int B,
+                                            int C, int HW) {
+  __shared__ float tile[32][33];
+  // grid: (HW/32, C/32, B)
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int pix = p0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (pix < HW && c < C) ? __half2float(x[((long)b * HW + pix) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, pix = p0 + threadIdx.x;
+    if (pix < HW && c < C) y[((long)b * C + c) * HW + pix] = tile[threadIdx.x][j];
+  }
+}
+
+// F.interpolate(scale_factor=2, mode="nearest") (openaimodel.py:107), NHWC, 8 channels/thread
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W,
+                                  int CV) {
+  const long total = (long)B * 4 * H * W * CV;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long t = i / CV;
+    const int ox = (int)(t % (2 * W));
+    t /= (2 * W);
+    const int oy = (int)(t % (2 * H));
+    const int b = (int)(t / (2 * H));
+    y[i] = x[(((long)b * H + (oy >> 1)) * W + (ox >> 1)) * CV + cv];
+  }
+}
+
+// im2col for conv3x3 stride 2 pad 1 (openaimodel.py:130-134): out [B*Ho*Wo, 9*C]
+__global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W,
+                                 int CV) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long total = (long)B * Ho * Wo * 9 * CV;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long t = i / CV;
+    const int tap = (int)(t % 9);
+    t /= 9;
+    const int ox = (int)(t % Wo);
+    t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const int iy = 2 * oy - 1 + tap / 3, ix = 2 * ox - 1 + tap % 3;
+    y[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? x[(((long)b * H + iy) * W + ix) * CV + cv] : zero;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// UniFusion Fourier embedder + null substitution + text concat
+// (text_grounding_net.py:216-225, 248-276; util.py:12-26).  One block per (b, slot) row.
+// ---------------------------------------------------------------------------------------------
+__constant__ float c_freqs[16];
+
+__global__ void __launch_bounds__(256)
+fourier_embed_kernel(const float* __restrict__ coords, const float* __restrict__ masks,
+                     const float* __restrict__ text, const float* __restrict__ null_text,
+                     const float* __restrict__ null_pos, __half* __restrict__ out, int D,
+                     int text_dim, int out_ld, int mask_mode, int dropped) {
+  __shared__ float red[8];
+  __shared__ float s_mpos;
+  const int row = blockIdx.x;
+  const float m = masks[row];
+  const float* xr = coords + (long)row * D;
+  float mpos;
+  if (dropped) {
+    mpos = 0.f;
+  } else if (mask_mode == 0) {
+    mpos = m;
+  } else {
+    float s = 0.f;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) s += xr[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+      s_mpos = ((t + m) > 0.f) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    mpos = s_mpos;
+  }
+  __half* orow = out + (long)row * out_ld;
+  if (text) {
+    for (int j = threadIdx.x; j < text_dim; j += blockDim.x)
+      orow[j] = __float2half(text[(long)row * text_dim + j] * m + (1.f - m) * null_text[j]);
+  }
+  const int E = 32 * D;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const int k = e / (2 * D);
+    const int rem = e - k * 2 * D;
+    const int is_cos = rem >= D;
+    const int j = is_cos ? rem - D : rem;
+    const float arg = c_freqs[k] * xr[j];
+    const float val = is_cos ? cosf(arg) : sinf(arg);
+    orow[text_dim + e] = __float2half(val * mpos + (1.f - mpos) * null_pos[e]);
+  }
+}
+
+// timestep_embedding (util.py:160-180): [cos(t f) | sin(t f)], f_k = exp(-ln(1e4) k / half)
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, __half* __restrict__ out, int B,
+                                          int dim) {
+  const int half_dim = dim >> 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half_dim) return;
+  const int b = i / half_dim, k = i - b * half_dim;
+  const float f = expf(-9.210340371976184f * (float)k / (float)half_dim);
+  const float arg = t[b] * f;
+  out[(long)b * dim + k] = __float2half(cosf(arg));
+  out[(long)b * dim + half_dim + k] = __float2half(sinf(arg));
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused PLMS update (plms.py:121-165; plms_instance.py:166-210)
+// ---------------------------------------------------------------------------------------------
+__global__ void plms_update_kernel(const float* __restrict__ x, const float* __restrict__ e_c,
+                                   const float* __restrict__ e_u, float gs, const float* __restrict__ o1,
+                                   const float* __restrict__ o2, const float* __restrict__ o3, float c0,
+                                   float c1, float c2, float c3, float sqrt_at, float sqrt_aprev,
+                                   float sqrt_1m_at, float sqrt_1m_aprev, float* __restrict__ e_out,
+                                   float* __restrict__ x_out, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float e = e_c[i];
+    if (e_u) {
+      const float u = e_u[i];
+      e = u + gs * (e - u);
+    }
+    float ep = c0 * e;
+    if (o1) ep += c1 * o1[i];
+    if (o2) ep += c2 * o2[i];
+    if (o3) ep += c3 * o3[i];
+    const float pred_x0 = (x[i] - sqrt_1m_at * ep) / sqrt_at;
+    const float xp = sqrt_aprev * pred_x0 + sqrt_1m_aprev * ep;
+    if (e_out) e_out[i] = e;
+    x_out[i] = xp;
+  }
+}
+
+__global__ void latent_mean_kernel(const float* const* __restrict__ xs, int count, float* __restrict__ out,
+                                   long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < count; ++k) s += xs[k][i];
+    out[i] = s / (float)count;
+  }
+}
+
+static inline int grid_for(long total, int threads) {
+  long g = (total + threads - 1) / threads;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace idiff
+
+using namespace idiff;
+
+extern "C" int idiff_scaleu_concat(const void* h, const void* skip, void* out, const float* b1, float s,
+                                   float* coef_ws, int batch, int height, int width, int c1, int c2,
+                                   void* stream) {
+  IDIFF_REQUIRE(h && skip && out && b1 && coef_ws, "idiff_scaleu_concat: null pointer argument");
+  IDIFF_REQUIRE(c1 % 8 == 0 && c2 % 8 == 0, "idiff_scaleu_concat: channels must be multiples of 8");
+  IDIFF_REQUIRE(height <= 128 && width <= 128, "idiff_scaleu_concat: H,W <= 128 supported");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  IDIFF_CHECK_CUDA(cudaMemsetAsync(coef_ws, 0, sizeof(float) * 8 * (size_t)batch * c2, st));
+  const int hw = height * width;
+  int ppb = (32768 + c2 - 1) / c2;
+  const int chunks = (hw + ppb - 1) / ppb;
+  scaleu_coef_kernel<<<dim3(chunks, batch), SU_THREADS, 0, st>>>(reinterpret_cast<const __half2*>(skip),
+                                                              coef_ws, height, width, c2, ppb);
+  const long total = (long)batch * hw * ((c1 + c2) / 8);
+  scaleu_apply_kernel<<<grid_for(total, SU_THREADS), SU_THREADS, 0, st>>>(
+      reinterpret_cast<const uint4*>(h), reinterpret_cast<const uint4*>(skip), reinterpret_cast<uint4*>(out),
+      b1, coef_ws, s - 1.0f, batch, height, width, c1, c2);
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int idiff_nchw_f32_to_nhwc_f16(const float* x, void* y, int batch, int c, int hw, int c_pad,
+                                          void* stream) {
+  IDIFF_REQUIRE(x && y && c_pad >= c, "idiff_nchw_f32_to_nhwc_f16: bad arguments");
+  const long total = (long)batch * hw * c_pad;
+  nchw_f32_to_nhwc_f16_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__half*>(y), batch, c, hw, c_pad);
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int idiff_nhwc_f16_to_nchw_f32(const void* x, float* y, int batch, int c, int hw, void* stream) {
+  IDIFF_REQUIRE(x && y, "idiff_nhwc_f16_to_nchw_f32: null pointer argument");
+  dim3 grid((hw + 31) / 32, (c + 31) / 32, batch);
+  nhwc_f16_to_nchw_f32_kernel<<<grid, dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), y, batch, c, hw);
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int idiff_upsample_nearest2x(const void* x, void* y, int batch, int h, int w, int c, void* stream) {
+  IDIFF_REQUIRE(x && y && c % 8 == 0, "idiff_upsample_nearest2x: bad arguments");
+  const long total = (long)batch * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), batch, h, w, c / 8);
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int idiff_im2col_s2(const void* x, void* y, int batch, int h, int w, int c, void* stream) {
+  IDIFF_REQUIRE(x && y && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "idiff_im2col_s2: bad arguments");
+  const long total = (long)batch * (h / 2) * (w / 2) * 9 * (c / 8);
+  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), batch, h, w, c / 8);
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int idiff_fourier_embed(const float* coords, const float* masks, const float* text,
+                                   const float* null_text, const float* null_pos, void* out, int rows,
+                                   int coord_dim, int text_dim, int out_ld, int mask_mode, int dropped,
+                                   void* stream) {
+  IDIFF_REQUIRE(coords && masks && null_pos && out, "idiff_fourier_embed: null pointer argument");
+  IDIFF_REQUIRE(!text || null_text, "idiff_fourier_embed: text given without null_text");
+  static bool freqs_set = false;
+  if (!freqs_set) {
+    float f[16];
+    for (int k = 0; k < 16; ++k) f[k] = (float)pow(100.0, (double)k / 16.0);  // util.py:17
+    IDIFF_CHECK_CUDA(cudaMemcpyToSymbol(c_freqs, f, sizeof(f)));
+    freqs_set = true;
+  }
+  fourier_embed_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      coords, masks, text, null_text, null_pos, reinterpret_cast<__half*>(out), coord_dim,
+      text ? text_dim : 0, out_ld, mask_mode, dropped);
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int idiff_timestep_embedding(const float* t, void* out, int batch, int dim, void* stream) {
+  IDIFF_REQUIRE(t && out && dim % 2 == 0, "idiff_timestep_embedding: bad arguments");
+  const int total = batch * dim / 2;
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      t, reinterpret_cast<__half*>(out), batch, dim);
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int idiff_plms_update(const float* x, const float* e_c, const float* e_u, float gs,
+                                 const float* old1, const float* old2, const float* old3, float c0,
+                                 float c1, float c2, float c3, float a_t, float a_prev,
+                                 float sqrt_one_minus_at, float* e_out, float* x_out, long n, void* stream) {
+  IDIFF_REQUIRE(x && e_c && x_out && n > 0, "idiff_plms_update: bad arguments");
+  plms_update_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, e_c, e_u, gs, old1, old2, old3, c0, c1, c2, c3, sqrtf(a_t), sqrtf(a_prev), sqrt_one_minus_at,
+      sqrtf(1.0f - a_prev), e_out, x_out, n);
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int idiff_latent_mean(const float* const* xs_dev, int count, float* out, long n, void* stream) {
+  IDIFF_REQUIRE(xs_dev && out && count > 0, "idiff_latent_mean: bad arguments");
+  latent_mean_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(xs_dev, count, out, n);
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

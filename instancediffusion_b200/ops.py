@@ -1,0 +1,265 @@
+"""Thin torch-tensor front end of the C ABI (include/idiff_b200.h).
+
+torch is used only for device memory and the current stream; all arithmetic happens in
+libidiff_b200.so.  Every function enqueues on torch's current CUDA stream and returns the output
+tensor without synchronising.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AttnArgs, GemmArgs, check
+
+HALF = torch.float16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.IdiffError(f"{name} must be a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise _lib.IdiffError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.dim() >= 1 and t.stride(-1) != 1:
+        raise _lib.IdiffError(f"{name} must be contiguous in its last dimension")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+         out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+         gate: float = 1.0, rowadd: Optional[torch.Tensor] = None, rows_per_batch: int = 0,
+         geglu: bool = False, silu: bool = False,
+         conv: Optional[Tuple[int, int, int, int]] = None,
+         out_nchw: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = epilogue(a @ w.T).  a: fp16 [M,K] (or NHWC [B,H,W,Cin] flattened with conv=(B,H,W,Cin));
+    w: fp16 [N,K].  See idiff_gemm in include/idiff_b200.h."""
+    lib = _lib.load()
+    _req(a, HALF, "a")
+    _req(w, HALF, "w")
+    N, K = w.shape
+    if conv is not None:
+        B, H, Wd, Cin = conv
+        M = B * H * Wd
+        a2 = a.reshape(M, Cin)
+        lda = Cin
+        if not a2.is_contiguous():
+            raise _lib.IdiffError("conv activation must be contiguous NHWC")
+    else:
+        a2 = a.reshape(-1, a.shape[-1])
+        M = a2.shape[0]
+        lda = a2.stride(0)
+        if a2.shape[1] != K:
+            raise _lib.IdiffError(f"gemm: K mismatch a[{a2.shape}] w[{w.shape}]")
+    n_out = N // 2 if geglu else N
+    flags = (1 if geglu else 0) | (2 if silu else 0)
+    args = GemmArgs()
+    if out_nchw is not None:
+        _req(out_nchw, torch.float32, "out_nchw")
+        flags |= 4
+        args.out = out_nchw.data_ptr()
+        args.ldo = 0
+        result = out_nchw
+    else:
+        if out is None:
+            out = torch.empty((M, n_out), dtype=HALF, device=a.device)
+        _req(out, HALF, "out")
+        args.out = out.data_ptr()
+        args.ldo = out.stride(0) if out.dim() == 2 else n_out
+        result = out
+    args.a = a2.data_ptr()
+    args.w = w.data_ptr()
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+    args.bias = _ptr(bias)
+    if rowadd is not None:
+        _req(rowadd, HALF, "rowadd")
+    args.rowadd = _ptr(rowadd)
+    if residual is not None:
+        _req(residual, HALF, "residual")
+        args.ldr = residual.stride(0)
+    args.residual = _ptr(residual)
+    args.gate = float(gate)
+    args.M, args.N, args.K = M, N, K
+    args.lda, args.ldw = lda, w.stride(0)
+    args.rows_per_batch = rows_per_batch
+    args.flags = flags
+    if conv is not None:
+        args.conv_b, args.conv_h, args.conv_w, args.conv_cin = conv
+    check(lib.idiff_gemm(C.byref(args), _stream()), "idiff_gemm")
+    return result
+
+
+def attention(q: torch.Tensor, k0: torch.Tensor, v0: torch.Tensor, *, batch: int, heads: int,
+              head_dim: int, nq: int, n0: int, scale: float,
+              k1: Optional[torch.Tensor] = None, v1: Optional[torch.Tensor] = None, n1: int = 0,
+              kv1_batch: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T scale) v over segment 0 (+ optional segment 1) keys.  q/k/v are 2-D fp16 views
+    [batch*rows, >= heads*head_dim] (row stride = .stride(0)); returns fp16 [batch*nq, heads*head_dim]."""
+    lib = _lib.load()
+    for name, t in (("q", q), ("k0", k0), ("v0", v0)):
+        _req(t, HALF, name)
+    C_ = heads * head_dim
+    if out is None:
+        out = torch.empty((batch * nq, C_), dtype=HALF, device=q.device)
+    a = AttnArgs()
+    a.q, a.k0, a.v0 = q.data_ptr(), k0.data_ptr(), v0.data_ptr()
+    a.q_ld, a.k0_ld, a.v0_ld = q.stride(0), k0.stride(0), v0.stride(0)
+    if n1 > 0:
+        _req(k1, HALF, "k1")
+        _req(v1, HALF, "v1")
+        a.k1, a.v1 = k1.data_ptr(), v1.data_ptr()
+        a.k1_ld, a.v1_ld = k1.stride(0), v1.stride(0)
+    a.out = out.data_ptr()
+    a.out_ld = out.stride(0)
+    a.batch, a.heads, a.head_dim = batch, heads, head_dim
+    a.nq, a.n0, a.n1 = nq, n0, n1
+    a.kv1_batch = kv1_batch if kv1_batch else batch
+    a.scale = float(scale)
+    check(lib.idiff_attention(C.byref(a), _stream()), "idiff_attention")
+    return out
+
+
+def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, batch: int, hw: int,
+              groups: int = 32, eps: float = 1e-5, silu: bool = False,
+              out: Optional[torch.Tensor] = None, stats_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x, HALF, "x")
+    Cc = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    if stats_ws is None:
+        stats_ws = torch.empty(batch * groups * 2, dtype=torch.float32, device=x.device)
+    check(lib.idiff_groupnorm(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                              stats_ws.data_ptr(), batch, hw, Cc, groups, eps, int(silu), _stream()),
+          "idiff_groupnorm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x, HALF, "x")
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+        raise _lib.IdiffError("layernorm input must be contiguous")
+    if out is None:
+        out = torch.empty_like(x2)
+    check(lib.idiff_layernorm(x2.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                              x2.shape[0], x2.shape[1], eps, _stream()), "idiff_layernorm")
+    return out
+
+
+def scaleu_concat(h: torch.Tensor, skip: torch.Tensor, b1: torch.Tensor, s: float, *, batch: int,
+                  height: int, width: int, out: Optional[torch.Tensor] = None,
+                  coef_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _req(h, HALF, "h")
+    _req(skip, HALF, "skip")
+    c1, c2 = h.shape[-1], skip.shape[-1]
+    if out is None:
+        out = torch.empty((batch * height * width, c1 + c2), dtype=HALF, device=h.device)
+    if coef_ws is None:
+        coef_ws = torch.empty(batch * c2 * 8, dtype=torch.float32, device=h.device)
+    check(lib.idiff_scaleu_concat(h.data_ptr(), skip.data_ptr(), out.data_ptr(), b1.data_ptr(), float(s),
+                                  coef_ws.data_ptr(), batch, height, width, c1, c2, _stream()),
+          "idiff_scaleu_concat")
+    return out
+
+
+def nchw_f32_to_nhwc_f16(x: torch.Tensor, c_pad: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    B, Cc, H, W = x.shape
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty((B * H * W, c_pad), dtype=HALF, device=x.device)
+    check(lib.idiff_nchw_f32_to_nhwc_f16(x.data_ptr(), out.data_ptr(), B, Cc, H * W, c_pad, _stream()),
+          "idiff_nchw_f32_to_nhwc_f16")
+    return out
+
+
+def nhwc_f16_to_nchw_f32(x: torch.Tensor, batch: int, h: int, w: int) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x, HALF, "x")
+    Cc = x.shape[-1]
+    out = torch.empty((batch, Cc, h, w), dtype=torch.float32, device=x.device)
+    check(lib.idiff_nhwc_f16_to_nchw_f32(x.data_ptr(), out.data_ptr(), batch, Cc, h * w, _stream()),
+          "idiff_nhwc_f16_to_nchw_f32")
+    return out
+
+
+def upsample_nearest2x(x: torch.Tensor, batch: int, h: int, w: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x, HALF, "x")
+    Cc = x.shape[-1]
+    if out is None:
+        out = torch.empty((batch * 4 * h * w, Cc), dtype=HALF, device=x.device)
+    check(lib.idiff_upsample_nearest2x(x.data_ptr(), out.data_ptr(), batch, h, w, Cc, _stream()),
+          "idiff_upsample_nearest2x")
+    return out
+
+
+def im2col_s2(x: torch.Tensor, batch: int, h: int, w: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x, HALF, "x")
+    Cc = x.shape[-1]
+    if out is None:
+        out = torch.empty((batch * (h // 2) * (w // 2), 9 * Cc), dtype=HALF, device=x.device)
+    check(lib.idiff_im2col_s2(x.data_ptr(), out.data_ptr(), batch, h, w, Cc, _stream()), "idiff_im2col_s2")
+    return out
+
+
+def fourier_embed(coords: torch.Tensor, masks: torch.Tensor, null_pos: torch.Tensor, out: torch.Tensor, *,
+                  text: Optional[torch.Tensor] = None, null_text: Optional[torch.Tensor] = None,
+                  mask_mode: int = 0, dropped: bool = False) -> torch.Tensor:
+    """coords fp32 [rows, D]; masks fp32 [rows]; out fp16 [rows, text_dim + 32*D] (row stride free)."""
+    lib = _lib.load()
+    _req(coords, torch.float32, "coords")
+    _req(masks, torch.float32, "masks")
+    _req(out, HALF, "out")
+    rows, D = coords.shape
+    text_dim = text.shape[-1] if text is not None else 0
+    check(lib.idiff_fourier_embed(coords.data_ptr(), masks.data_ptr(), _ptr(text), _ptr(null_text),
+                                  null_pos.data_ptr(), out.data_ptr(), rows, D, text_dim, out.stride(0),
+                                  mask_mode, int(dropped), _stream()), "idiff_fourier_embed")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _req(t, torch.float32, "t")
+    B = t.shape[0]
+    if out is None:
+        out = torch.empty((B, dim), dtype=HALF, device=t.device)
+    check(lib.idiff_timestep_embedding(t.data_ptr(), out.data_ptr(), B, dim, _stream()),
+          "idiff_timestep_embedding")
+    return out
+
+
+def plms_update(x: torch.Tensor, e_c: torch.Tensor, e_u: Optional[torch.Tensor], gs: float,
+                olds, coefs, a_t: float, a_prev: float, sqrt_one_minus_at: float,
+                e_out: Optional[torch.Tensor], x_out: torch.Tensor) -> None:
+    lib = _lib.load()
+    o = list(olds) + [None] * (3 - len(olds))
+    c = list(coefs) + [0.0] * (4 - len(coefs))
+    check(lib.idiff_plms_update(x.data_ptr(), e_c.data_ptr(), _ptr(e_u), float(gs), _ptr(o[0]), _ptr(o[1]),
+                                _ptr(o[2]), c[0], c[1], c[2], c[3], float(a_t), float(a_prev),
+                                float(sqrt_one_minus_at), _ptr(e_out), x_out.data_ptr(), x.numel(), _stream()),
+          "idiff_plms_update")
+
+
+def latent_mean(xs, out: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    ptrs = torch.tensor([t.data_ptr() for t in xs], dtype=torch.int64).to(out.device)
+    check(lib.idiff_latent_mean(ptrs.data_ptr(), len(xs), out.data_ptr(), out.numel(), _stream()),
+          "idiff_latent_mean")
+    return out

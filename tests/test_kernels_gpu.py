@@ -1,0 +1,340 @@
+"""Per-kernel numerics: every C-ABI entry point against a plain torch fp32 reference of the same op
+on the same seeded inputs (the fp16-rounded inputs are upcast, so only accumulation order and the
+fp16 output rounding differ).  Tolerances are stated per test.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from instancediffusion_b200 import ops
+    return ops
+
+
+def _randn(shape, dev, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev)
+
+
+def _check(got, ref, rtol, atol, what):
+    got = got.float()
+    ref = ref.float()
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = (err > tol)
+    max_err = err.max().item()
+    ref_max = ref.abs().max().item()
+    print(f"[{what}] max_abs_err={max_err:.3e} ref_max={ref_max:.3e} bad={int(bad.sum())}/{bad.numel()}")
+    assert not bad.any(), f"{what}: max err {max_err:.3e} (ref max {ref_max:.3e}), {int(bad.sum())} bad"
+
+
+# --------------------------------------------------------------------------------------------
+# GEMM (linear)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 320, 320), (4096, 640, 320), (100, 320, 1280),
+                                   (8, 1280, 320), (1024, 1280, 5120), (77, 640, 768)])
+def test_gemm_linear(cuda_device, M, N, K):
+    ops = _ops()
+    a = _randn((M, K), cuda_device, 1.0, 1).half()
+    w = _randn((N, K), cuda_device, 1.0 / math.sqrt(K), 2).half()
+    bias = _randn((N,), cuda_device, 0.5, 3)
+    out = ops.gemm(a, w, bias)
+    ref = a.float() @ w.float().t() + bias
+    # fp32 accumulate, fp16 output rounding: 1e-3 relative + small absolute
+    _check(out, ref, 2e-3, 2e-3, f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_residual_gate_silu(cuda_device):
+    ops = _ops()
+    M, N, K = 512, 320, 640
+    a = _randn((M, K), cuda_device, 1.0, 1).half()
+    w = _randn((N, K), cuda_device, 1.0 / math.sqrt(K), 2).half()
+    bias = _randn((N,), cuda_device, 0.5, 3)
+    res = _randn((M, N), cuda_device, 1.0, 4).half()
+    out = ops.gemm(a, w, bias, residual=res, gate=0.37)
+    ref = res.float() + 0.37 * (a.float() @ w.float().t() + bias)
+    _check(out, ref, 2e-3, 2e-3, "gemm residual+gate")
+    out = ops.gemm(a, w, bias, silu=True)
+    ref = F.silu(a.float() @ w.float().t() + bias)
+    _check(out, ref, 2e-3, 2e-3, "gemm silu")
+    # per-batch row vector (ResBlock emb add), 4 batches of 128 rows
+    radd = _randn((4, N), cuda_device, 1.0, 5).half()
+    out = ops.gemm(a, w, bias, rowadd=radd, rows_per_batch=128)
+    ref = a.float() @ w.float().t() + bias + radd.float().repeat_interleave(128, dim=0)
+    _check(out, ref, 2e-3, 2e-3, "gemm rowadd")
+
+
+@pytest.mark.parametrize("M,C", [(256, 320), (1000, 640)])
+def test_gemm_geglu(cuda_device, M, C):
+    """GEGLU (attention.py:36-43): proj -> chunk(2) -> x * gelu(gate); weight rows are packed per 64."""
+    from instancediffusion_b200.packing import pack_geglu
+    ops = _ops()
+    inner = 4 * C
+    a = _randn((M, C), cuda_device, 1.0, 1).half()
+    w = _randn((2 * inner, C), cuda_device, 1.0 / math.sqrt(C), 2).half()
+    bias = _randn((2 * inner,), cuda_device, 0.5, 3)
+    wp, bp = pack_geglu(w, bias)
+    out = ops.gemm(a, wp, bp, geglu=True)
+    h = a.float() @ w.float().t() + bias
+    x, gate = h.chunk(2, dim=-1)
+    ref = x * F.gelu(gate)
+    _check(out, ref, 3e-3, 3e-3, f"geglu {M}x{C}")
+
+
+# --------------------------------------------------------------------------------------------
+# conv3x3 (implicit GEMM through 4-D TMA)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 64, 64, 64, 128), (2, 32, 32, 320, 320), (2, 16, 16, 640, 1280),
+                                            (4, 8, 8, 1280, 1280), (3, 8, 8, 128, 64), (1, 24, 24, 64, 64),
+                                            (2, 12, 12, 64, 64), (1, 96, 96, 64, 64)])
+def test_conv3x3(cuda_device, B, H, W, Cin, Cout):
+    from instancediffusion_b200.packing import pack_conv3x3
+    ops = _ops()
+    x = _randn((B, Cin, H, W), cuda_device, 1.0, 1).half()
+    w = _randn((Cout, Cin, 3, 3), cuda_device, 1.0 / math.sqrt(9 * Cin), 2).half()
+    bias = _randn((Cout,), cuda_device, 0.5, 3)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().reshape(B * H * W, Cin)
+    out = ops.gemm(x_nhwc, pack_conv3x3(w), bias, conv=(B, H, W, Cin))
+    ref = F.conv2d(x.float(), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(B * H * W, Cout)
+    _check(out, ref, 2e-3, 2e-3, f"conv3x3 {B}x{H}x{W} {Cin}->{Cout}")
+
+
+def test_conv3x3_rowadd_and_nchw_out(cuda_device):
+    from instancediffusion_b200.packing import pack_conv3x3
+    ops = _ops()
+    B, H, W, Cin, Cout = 2, 64, 64, 320, 320
+    x = _randn((B, Cin, H, W), cuda_device, 1.0, 1).half()
+    w = _randn((Cout, Cin, 3, 3), cuda_device, 1.0 / math.sqrt(9 * Cin), 2).half()
+    bias = _randn((Cout,), cuda_device, 0.5, 3)
+    emb = _randn((B, Cout), cuda_device, 1.0, 4).half()
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().reshape(B * H * W, Cin)
+    out = ops.gemm(x_nhwc, pack_conv3x3(w), bias, conv=(B, H, W, Cin), rowadd=emb)
+    ref = F.conv2d(x.float(), w.float(), bias, padding=1) + emb.float()[:, :, None, None]
+    _check(out, ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout), 2e-3, 2e-3, "conv3x3 + emb")
+    # final conv 320 -> 4 with fp32 NCHW output (openaimodel.py:461-465)
+    w4 = _randn((4, Cin, 3, 3), cuda_device, 1.0 / math.sqrt(9 * Cin), 5).half()
+    b4 = _randn((4,), cuda_device, 0.5, 6)
+    w4p = torch.zeros((8, 9 * Cin), dtype=torch.float16, device=cuda_device)
+    w4p[:4] = pack_conv3x3(w4)
+    o = torch.empty((B, 4, H, W), dtype=torch.float32, device=cuda_device)
+    ops.gemm(x_nhwc, w4p[:4], b4, conv=(B, H, W, Cin), out_nchw=o)
+    ref = F.conv2d(x.float(), w4.float(), b4, padding=1)
+    _check(o, ref, 1e-3, 1e-3, "conv3x3 -> fp32 NCHW")
+
+
+def test_downsample_and_upsample_helpers(cuda_device):
+    from instancediffusion_b200.packing import pack_conv3x3
+    ops = _ops()
+    B, H, W, C = 2, 32, 32, 320
+    x = _randn((B, C, H, W), cuda_device, 1.0, 1).half()
+    w = _randn((C, C, 3, 3), cuda_device, 1.0 / math.sqrt(9 * C), 2).half()
+    bias = _randn((C,), cuda_device, 0.5, 3)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().reshape(B * H * W, C)
+    cols = ops.im2col_s2(x_nhwc, B, H, W)
+    out = ops.gemm(cols, pack_conv3x3(w), bias)
+    ref = F.conv2d(x.float(), w.float(), bias, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, C)
+    _check(out, ref, 2e-3, 2e-3, "downsample conv (im2col s2)")
+    up = ops.upsample_nearest2x(x_nhwc, B, H, W)
+    ref = F.interpolate(x.float(), scale_factor=2, mode="nearest").permute(0, 2, 3, 1).reshape(-1, C)
+    _check(up, ref, 0, 0, "upsample nearest 2x")
+
+
+# --------------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------------
+def _ref_attn(q, k, v, heads, scale):
+    B, Nq, C = q.shape
+    d = C // heads
+    qh = q.float().view(B, Nq, heads, d).transpose(1, 2)
+    kh = k.float().view(B, -1, heads, d).transpose(1, 2)
+    vh = v.float().view(B, -1, heads, d).transpose(1, 2)
+    s = (qh @ kh.transpose(-1, -2)) * scale
+    o = s.softmax(-1) @ vh
+    return o.transpose(1, 2).reshape(B * Nq, C)
+
+
+@pytest.mark.parametrize("B,N,d", [(2, 256, 40), (1, 4096, 40), (2, 1024, 80), (3, 256, 160), (4, 64, 160), (1, 200, 80)])
+def test_self_attention_fused_qkv(cuda_device, B, N, d):
+    ops = _ops()
+    heads = 8
+    C = heads * d
+    qkv = _randn((B * N, 3 * C), cuda_device, 1.0, 1).half()
+    out = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], batch=B, heads=heads, head_dim=d,
+                        nq=N, n0=N, scale=d ** -0.5)
+    q, k, v = (qkv[:, i * C:(i + 1) * C].reshape(B, N, C) for i in range(3))
+    ref = _ref_attn(q, k, v, heads, d ** -0.5)
+    # P is rounded to fp16 before the PV product (as in flash attention); output fp16
+    _check(out, ref, 3e-3, 3e-3, f"self-attn B{B} N{N} d{d}")
+
+
+@pytest.mark.parametrize("B,N,d,shared", [(2, 256, 40, False), (2, 1024, 80, True), (2, 64, 160, False), (1, 4096, 40, True)])
+def test_gated_attention_two_segments(cuda_device, B, N, d, shared):
+    """Keys = N visual tokens + 184 object tokens, queries = visual rows only (attention.py:304-308)."""
+    ops = _ops()
+    heads = 8
+    C = heads * d
+    qkv = _randn((B * N, 3 * C), cuda_device, 1.0, 1).half()
+    B1 = 1 if shared else B
+    okv = _randn((B1 * 184, 2 * C), cuda_device, 1.0, 2).half()
+    out = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], batch=B, heads=heads, head_dim=d,
+                        nq=N, n0=N, scale=d ** -0.5, k1=okv[:, :C], v1=okv[:, C:], n1=184, kv1_batch=B1)
+    q, k, v = (qkv[:, i * C:(i + 1) * C].reshape(B, N, C) for i in range(3))
+    ok = okv[:, :C].reshape(B1, 184, C).expand(B, 184, C)
+    ov = okv[:, C:].reshape(B1, 184, C).expand(B, 184, C)
+    ref = _ref_attn(q, torch.cat([k, ok], 1), torch.cat([v, ov], 1), heads, d ** -0.5)
+    _check(out, ref, 3e-3, 3e-3, f"gated-attn B{B} N{N} d{d} shared={shared}")
+
+
+@pytest.mark.parametrize("B,N,d", [(2, 1024, 80), (2, 4096, 40), (2, 64, 160)])
+def test_cross_attention_77_keys(cuda_device, B, N, d):
+    ops = _ops()
+    heads = 8
+    C = heads * d
+    q = _randn((B * N, C), cuda_device, 1.0, 1).half()
+    kv = _randn((B * 77, 2 * C), cuda_device, 1.0, 2).half()
+    out = ops.attention(q, kv[:, :C], kv[:, C:], batch=B, heads=heads, head_dim=d, nq=N, n0=77, scale=d ** -0.5)
+    ref = _ref_attn(q.reshape(B, N, C), kv[:, :C].reshape(B, 77, C), kv[:, C:].reshape(B, 77, C), heads, d ** -0.5)
+    _check(out, ref, 3e-3, 3e-3, f"cross-attn B{B} N{N} d{d}")
+
+
+# --------------------------------------------------------------------------------------------
+# normalisation
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,HW,C,silu,eps", [(2, 4096, 320, True, 1e-5), (2, 1024, 960, True, 1e-5), (3, 64, 2560, True, 1e-5),
+                                             (2, 256, 1280, False, 1e-6), (1, 1024, 1920, True, 1e-5)])
+def test_groupnorm(cuda_device, B, HW, C, silu, eps):
+    ops = _ops()
+    x = (_randn((B * HW, C), cuda_device, 1.5, 1) + 0.3).half()
+    gamma = 1.0 + _randn((C,), cuda_device, 0.2, 2)
+    beta = _randn((C,), cuda_device, 0.2, 3)
+    out = ops.groupnorm(x, gamma, beta, batch=B, hw=HW, groups=32, eps=eps, silu=silu)
+    xr = x.float().view(B, HW, C).permute(0, 2, 1)
+    ref = F.group_norm(xr, 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1).reshape(B * HW, C)
+    _check(out, ref, 2e-3, 2e-3, f"groupnorm B{B} HW{HW} C{C}")
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 320), (1000, 640), (77, 1280)])
+def test_layernorm(cuda_device, rows, C):
+    ops = _ops()
+    x = (_randn((rows, C), cuda_device, 1.5, 1) + 0.3).half()
+    gamma = 1.0 + _randn((C,), cuda_device, 0.2, 2)
+    beta = _randn((C,), cuda_device, 0.2, 3)
+    out = ops.layernorm(x, gamma, beta, 1e-5)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    _check(out, ref, 2e-3, 2e-3, f"layernorm {rows}x{C}")
+
+
+# --------------------------------------------------------------------------------------------
+# ScaleU / Fourier filter
+# --------------------------------------------------------------------------------------------
+def _fourier_filter_ref(x, threshold, scale):
+    """Restatement of openaimodel.py:25-48 in fp32/complex64."""
+    import torch.fft as fft
+    B, C, H, W = x.shape
+    xf = fft.fftshift(fft.fftn(x.float(), dim=(-2, -1)), dim=(-2, -1))
+    mask = torch.ones((B, C, H, W), device=x.device)
+    crow, ccol = H // 2, W // 2
+    mask[..., crow - threshold:crow + threshold, ccol - threshold:ccol + threshold] = scale
+    xf = fft.ifftshift(xf * mask, dim=(-2, -1))
+    return fft.ifftn(xf, dim=(-2, -1)).real
+
+
+@pytest.mark.parametrize("B,H,W,C1,C2", [(2, 8, 8, 1280, 1280), (2, 16, 16, 1280, 640), (1, 64, 64, 320, 320), (1, 24, 24, 64, 64)])
+def test_scaleu_concat(cuda_device, B, H, W, C1, C2):
+    ops = _ops()
+    h = _randn((B, C1, H, W), cuda_device, 1.0, 1).half()
+    skip = (_randn((B, C2, H, W), cuda_device, 1.0, 2) + 0.5).half()
+    b_param = _randn((C1,), cuda_device, 0.5, 3)
+    s_param = 0.4
+    b1 = torch.tanh(b_param) + 1
+    s = math.tanh(s_param) + 1
+    hn = h.permute(0, 2, 3, 1).reshape(B * H * W, C1).contiguous()
+    sn = skip.permute(0, 2, 3, 1).reshape(B * H * W, C2).contiguous()
+    out = ops.scaleu_concat(hn, sn, b1, s, batch=B, height=H, width=W)
+    ref_h = h.float() * b1[None, :, None, None]
+    ref_s = _fourier_filter_ref(skip, 1, s)
+    ref = torch.cat([ref_h, ref_s], 1).permute(0, 2, 3, 1).reshape(B * H * W, C1 + C2)
+    _check(out, ref, 2e-3, 2e-3, f"scaleu {B}x{H}x{W} {C1}+{C2}")
+
+
+# --------------------------------------------------------------------------------------------
+# small helpers
+# --------------------------------------------------------------------------------------------
+def test_layout_roundtrip(cuda_device):
+    ops = _ops()
+    x = _randn((3, 4, 64, 64), cuda_device, 1.0, 1)
+    y = ops.nchw_f32_to_nhwc_f16(x, 64)
+    ref = torch.zeros((3 * 4096, 64), device=cuda_device)
+    ref[:, :4] = x.permute(0, 2, 3, 1).reshape(-1, 4)
+    _check(y, ref.half(), 0, 0, "nchw->nhwc pad")
+    z = _randn((2 * 256, 320), cuda_device, 1.0, 2).half()
+    back = ops.nhwc_f16_to_nchw_f32(z, 2, 16, 16)
+    _check(back, z.float().view(2, 256, 320).permute(0, 2, 1).reshape(2, 320, 16, 16), 0, 0, "nhwc->nchw")
+
+
+def test_timestep_embedding(cuda_device):
+    ops = _ops()
+    t = torch.tensor([981.0, 1.0, 501.0, 21.0], device=cuda_device)
+    out = ops.timestep_embedding(t, 320)
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=cuda_device) / half)
+    args = t[:, None] * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    _check(out, ref, 0, 1.5e-3, "timestep_embedding")
+
+
+@pytest.mark.parametrize("D,mode,dropped", [(4, 0, False), (2, 0, True), (40, 1, False), (512, 1, False)])
+def test_fourier_embed(cuda_device, D, mode, dropped):
+    ops = _ops()
+    rows = 60
+    coords = torch.rand((rows, D), generator=torch.Generator().manual_seed(1)).to(cuda_device)
+    masks = (torch.arange(rows) % 3 != 0).float().to(cuda_device)
+    if mode == 1:
+        coords[masks == 0] = 0
+        coords[5] = 0.1  # padded slot with non-zero coords still counts as present (:267)
+    text = _randn((rows, 768), cuda_device, 1.0, 2)
+    null_text = _randn((768,), cuda_device, 1.0, 3)
+    null_pos = _randn((32 * D,), cuda_device, 1.0, 4)
+    out = torch.empty((rows, 768 + 32 * D), dtype=torch.float16, device=cuda_device)
+    ops.fourier_embed(coords, masks, null_pos, out, text=text, null_text=null_text, mask_mode=mode, dropped=dropped)
+    freqs = 100 ** (torch.arange(16, device=cuda_device) / 16)
+    emb = torch.cat([f(fr * coords) for fr in freqs for f in (torch.sin, torch.cos)], -1)
+    m = masks[:, None]
+    if dropped:
+        mp = torch.zeros_like(m)
+    elif mode == 0:
+        mp = m
+    else:
+        mp = ((coords.sum(-1, keepdim=True) + m) > 0).float()
+    ref = torch.cat([text * m + (1 - m) * null_text, emb * mp + (1 - mp) * null_pos], -1)
+    _check(out, ref, 1e-3, 2e-3, f"fourier_embed D{D} mode{mode} dropped={dropped}")
+
+
+def test_plms_update_and_mean(cuda_device):
+    ops = _ops()
+    n = (4, 4, 64, 64)
+    x, ec, eu, o1, o2, o3 = (_randn(n, cuda_device, 1.0, i) for i in range(6))
+    a_t, a_prev = 0.31, 0.42
+    s1 = math.sqrt(1 - a_t)
+    e_out = torch.empty_like(x)
+    x_out = torch.empty_like(x)
+    ops.plms_update(x, ec, eu, 7.5, [o1, o2, o3], [55 / 24, -59 / 24, 37 / 24, -9 / 24], a_t, a_prev, s1, e_out, x_out)
+    e = eu + 7.5 * (ec - eu)
+    ep = (55 * e - 59 * o1 + 37 * o2 - 9 * o3) / 24
+    pred = (x - s1 * ep) / math.sqrt(a_t)
+    ref = math.sqrt(a_prev) * pred + math.sqrt(1 - a_prev) * ep
+    _check(e_out, e, 1e-6, 1e-6, "plms e")
+    _check(x_out, ref, 1e-5, 1e-5, "plms x_prev")
+    m = torch.empty_like(x)
+    ops.latent_mean([x, ec, eu], m)
+    _check(m, (x + ec + eu) / 3, 1e-6, 1e-6, "latent mean")
