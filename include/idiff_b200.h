@@ -49,11 +49,12 @@ typedef struct {
   const void* w;        /* fp16 [N, K] (ldw)                                                    */
   void* out;            /* fp16 [M, N or N/2] (ldo)     | fp32 NCHW with IDIFF_OUT_F32_NCHW      */
   const float* bias;    /* [N] or NULL                                                          */
-  const void* rowadd;   /* fp16 [M / rows_per_batch, N] added per batch (ResBlock emb) or NULL  */
+  const void* rowadd;   /* fp16 [M / rows_per_batch, N] (row stride ldra) added per batch (ResBlock
+                           emb, openaimodel.py:246-256) or NULL                                 */
   const void* residual; /* fp16 [M, N_out] (ldr) or NULL: out = residual + gate * (...)         */
   float gate;           /* scale * tanh(alpha) of GatedSelfAttentionDense; 1 for plain residual */
   int M, N, K;
-  int lda, ldw, ldo, ldr;
+  int lda, ldw, ldo, ldr, ldra;
   int rows_per_batch;
   int flags;
   int conv_b, conv_h, conv_w, conv_cin;
@@ -153,6 +154,10 @@ int idiff_latent_mean(const float* const* xs_dev, int count, float* out, long n,
 /* timestep_embedding (util.py:160-180): out fp16 [B, dim] = [cos(t*f) | sin(t*f)],
    f_k = exp(-ln(1e4)*k/(dim/2)) */
 int idiff_timestep_embedding(const float* t, void* out, int batch, int dim, void* stream);
+
+/* y = x * sigmoid(x) on fp16 (the nn.SiLU in front of ResBlock.emb_layers, openaimodel.py:200, when
+   a ResBlock is driven through its module-level forward; the UNet path fuses it into a GEMM epilogue) */
+int idiff_silu_f16(const void* x, void* y, long n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ class GemmArgs(C.Structure):
         ("a", C.c_void_p), ("w", C.c_void_p), ("out", C.c_void_p), ("bias", C.c_void_p),
         ("rowadd", C.c_void_p), ("residual", C.c_void_p), ("gate", C.c_float),
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
-        ("lda", C.c_int), ("ldw", C.c_int), ("ldo", C.c_int), ("ldr", C.c_int),
+        ("lda", C.c_int), ("ldw", C.c_int), ("ldo", C.c_int), ("ldr", C.c_int), ("ldra", C.c_int),
         ("rows_per_batch", C.c_int), ("flags", C.c_int),
         ("conv_b", C.c_int), ("conv_h", C.c_int), ("conv_w", C.c_int), ("conv_cin", C.c_int),
     ]
@@ -61,6 +61,7 @@ SIGNATURES = {
     "idiff_plms_update": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _f, _vp, _vp, _l, _vp]),
     "idiff_latent_mean": (_i, [_vp, _i, _vp, _l, _vp]),
     "idiff_timestep_embedding": (_i, [_vp, _vp, _i, _i, _vp]),
+    "idiff_silu_f16": (_i, [_vp, _vp, _l, _vp]),
 }
 
 _lib = None

@@ -283,6 +283,11 @@ __global__ void latent_mean_kernel(const float* const* __restrict__ xs, int coun
   }
 }
 
+__global__ void silu_f16_kernel(const __half* __restrict__ x, __half* __restrict__ y, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = __float2half(silu_f(__half2float(x[i])));
+}
+
 static inline int grid_for(long total, int threads) {
   long g = (total + threads - 1) / threads;
   if (g > 148 * 16) g = 148 * 16;
@@ -396,6 +401,14 @@ extern "C" int idiff_plms_update(const float* x, const float* e_c, const float* 
 extern "C" int idiff_latent_mean(const float* const* xs_dev, int count, float* out, long n, void* stream) {
   IDIFF_REQUIRE(xs_dev && out && count > 0, "idiff_latent_mean: bad arguments");
   latent_mean_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(xs_dev, count, out, n);
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int idiff_silu_f16(const void* x, void* y, long n, void* stream) {
+  IDIFF_REQUIRE(x && y && n > 0, "idiff_silu_f16: bad arguments");
+  silu_f16_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), n);
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

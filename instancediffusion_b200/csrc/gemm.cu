@@ -32,7 +32,7 @@ struct GemmKParams {
   const __half* rowadd;
   const __half* residual;
   void* out;
-  int ldo, ldr, rows_per_batch, flags;
+  int ldo, ldr, ldra, rows_per_batch, flags;
   float gate;
 };
 
@@ -200,7 +200,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           float val = __uint_as_float(v[j]);
           if (col < p.N) {
             if (p.bias) val += __ldg(p.bias + col);
-            if (p.rowadd && row_ok) val += __half2float(p.rowadd[(long)batch_idx * p.N + col]);
+            if (p.rowadd && row_ok) val += __half2float(p.rowadd[(long)batch_idx * p.ldra + col]);
           }
           if (do_silu) val = silu_f(val);
           x[j] = val;
@@ -281,6 +281,7 @@ static int launch_gemm(const idiff_gemm_args* a, cudaStream_t stream) {
   p.out = a->out;
   p.ldo = a->ldo;
   p.ldr = a->ldr;
+  p.ldra = a->ldra > 0 ? a->ldra : a->N;
   p.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : a->M;
   p.flags = a->flags;
   p.gate = a->gate;

@@ -1,0 +1,78 @@
+"""Shared plumbing of the mirror modules: fp32 master parameters (so reference checkpoints load
+strict, utils/checkpoint.py:241-244) plus a lazily built pack of fp16/fp32 device tensors in the
+layouts the kernels want.  The pack is dropped whenever parameters may have changed
+(load_state_dict, .to()/.cuda())."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ... import _lib
+
+HALF = torch.float16
+
+
+class PackedModule(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self._pk = None
+
+    # -- cache invalidation -----------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        self._pk = None
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._pk = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def invalidate_pack(self):
+        for m in self.modules():
+            if isinstance(m, PackedModule):
+                m._pk = None
+
+    # -- pack access ------------------------------------------------------------------------
+    def pk(self):
+        if self._pk is None:
+            with torch.no_grad():
+                self._pk = self._pack()
+        return self._pk
+
+    def _pack(self):  # pragma: no cover - overridden
+        return {}
+
+
+def dev_of(p: torch.Tensor) -> torch.device:
+    if not p.is_cuda:
+        raise _lib.IdiffError(
+            "instancediffusion_b200 modules run only on a CUDA device (sm_100a); there is no CPU path. "
+            "Move the module with .cuda() first.")
+    return p.device
+
+
+def w16(p: torch.Tensor) -> torch.Tensor:
+    dev_of(p)
+    return p.detach().to(HALF).contiguous()
+
+
+def f32(p: torch.Tensor) -> torch.Tensor:
+    dev_of(p)
+    return p.detach().float().contiguous()
+
+
+def to_tokens(x: torch.Tensor):
+    """(B, N, C) any float dtype -> fp16 [B*N, C] contiguous."""
+    B, N, C = x.shape
+    return x.reshape(B * N, C).to(HALF).contiguous(), B, N
+
+
+def nchw_to_nhwc16(x: torch.Tensor):
+    """(B, C, H, W) -> fp16 [B*H*W, C] (boundary glue of the module-level API; the UNet fast path
+    converts once with idiff_nchw_f32_to_nhwc_f16)."""
+    B, C, H, W = x.shape
+    return x.permute(0, 2, 3, 1).reshape(B * H * W, C).to(HALF).contiguous(), B, H, W
+
+
+def nhwc16_to_nchw(y: torch.Tensor, B: int, H: int, W: int, dtype) -> torch.Tensor:
+    C = y.shape[-1]
+    return y.view(B, H, W, C).permute(0, 3, 1, 2).to(dtype).contiguous()

@@ -1,0 +1,324 @@
+"""Transformer operators of the UNet, same class names / constructor and forward signatures /
+state_dict keys as the reference's ldm/modules/attention.py, with the arithmetic in
+libidiff_b200.so (tcgen05 GEMM + flash attention + LayerNorm/GroupNorm kernels).
+
+Internal convention: token-major fp16 activations `[B*N, C]` (== NHWC), carried between the
+`_fwd` methods without any NCHW<->(B,HW,C) rearrange (attention.py:369,376 disappear).
+The public `forward` methods keep the reference layouts and are used for module-level parity.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...packing import pack_conv1x1, pack_geglu
+from ._base import HALF, PackedModule, f32, nchw_to_nhwc16, nhwc16_to_nchw, to_tokens, w16
+from .diffusionmodules.util import zero_module
+
+
+def exists(val):
+    return val is not None
+
+
+def default(val, d):
+    if exists(val):
+        return val
+    return d() if callable(d) else d
+
+
+# --------------------------------------------------------------------------------------------
+# feed-forward
+# --------------------------------------------------------------------------------------------
+class GEGLU(PackedModule):
+    """attention.py:36-43: proj -> chunk(2) -> x * gelu(gate) (exact erf GELU), fused into the
+    GEMM epilogue (value/gate rows interleaved per 64 at pack time)."""
+
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def _pack(self):
+        wp, bp = pack_geglu(w16(self.proj.weight), f32(self.proj.bias))
+        return {"w": wp, "b": bp}
+
+    def _fwd(self, x16: torch.Tensor) -> torch.Tensor:
+        p = self.pk()
+        return ops.gemm(x16, p["w"], p["b"], geglu=True)
+
+    def forward(self, x):
+        x16, B, N = to_tokens(x)
+        return self._fwd(x16).view(B, N, -1).to(x.dtype)
+
+
+class FeedForward(PackedModule):
+    """attention.py:46-63 with glu=True (the only configuration the UNet builds)."""
+
+    def __init__(self, dim, dim_out=None, mult=4, glu=False, dropout=0.):
+        super().__init__()
+        inner_dim = int(dim * mult)
+        dim_out = default(dim_out, dim)
+        if not glu:
+            raise NotImplementedError("FeedForward(glu=False) is not on the InstanceDiffusion path")
+        self.net = nn.Sequential(GEGLU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out))
+
+    def _pack(self):
+        return {"w2": w16(self.net[2].weight), "b2": f32(self.net[2].bias)}
+
+    def _fwd(self, x16, residual=None, gate=1.0, out=None):
+        """x16: LayerNorm-ed input.  Returns residual + gate * FF(x16) (or FF(x16) without residual)."""
+        p = self.pk()
+        h = self.net[0]._fwd(x16)
+        return ops.gemm(h, p["w2"], p["b2"], residual=residual, gate=gate, out=out)
+
+    def forward(self, x):
+        x16, B, N = to_tokens(x)
+        return self._fwd(x16).view(B, N, -1).to(x.dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------------
+class CrossAttention(PackedModule):
+    """attention.py:98-157.  K/V of the 77 text tokens are step-invariant: `project_kv` is hoisted
+    by the UNet (once per prompt), `_fwd` then needs only the Q projection."""
+
+    def __init__(self, query_dim, key_dim, value_dim, heads=8, dim_head=64, dropout=0, efficient_attention=False):
+        super().__init__()
+        inner_dim = dim_head * heads
+        self.scale = dim_head ** -0.5
+        self.heads = heads
+        self.dim_head = dim_head
+        self.efficient_attention = efficient_attention
+        self.to_q = nn.Linear(query_dim, inner_dim, bias=False)
+        self.to_k = nn.Linear(key_dim, inner_dim, bias=False)
+        self.to_v = nn.Linear(value_dim, inner_dim, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Dropout(dropout))
+
+    def _pack(self):
+        return {
+            "wq": w16(self.to_q.weight),
+            "wkv": torch.cat([w16(self.to_k.weight), w16(self.to_v.weight)], 0).contiguous(),
+            "wo": w16(self.to_out[0].weight),
+            "bo": f32(self.to_out[0].bias),
+        }
+
+    def project_kv(self, ctx16: torch.Tensor) -> torch.Tensor:
+        """ctx16 fp16 [B*M, key_dim] -> [B*M, 2*inner] = [K | V]."""
+        return ops.gemm(ctx16, self.pk()["wkv"])
+
+    def _fwd(self, x16, kv, B, N, M, residual=None, out=None):
+        p = self.pk()
+        C = self.heads * self.dim_head
+        q = ops.gemm(x16, p["wq"])
+        a = ops.attention(q, kv[:, :C], kv[:, C:2 * C], batch=B, heads=self.heads, head_dim=self.dim_head,
+                          nq=N, n0=M, scale=self.scale)
+        return ops.gemm(a, p["wo"], p["bo"], residual=residual, out=out)
+
+    def forward(self, x, key, value, mask=None):
+        if mask is not None:
+            raise NotImplementedError("CrossAttention mask is unused on the shipped sampling path")
+        if key is not value:
+            raise NotImplementedError("CrossAttention expects key is value (attention.py:336 passes context twice)")
+        x16, B, N = to_tokens(x)
+        c16, _, M = to_tokens(key)
+        return self._fwd(x16, self.project_kv(c16), B, N, M).view(B, N, -1).to(x.dtype)
+
+
+class SelfAttention(PackedModule):
+    """attention.py:160-282 (efficient_attention path; the instance attention-mask builder at
+    :187-255 is dead under every shipped config)."""
+
+    def __init__(self, query_dim, heads=8, dim_head=64, dropout=0., efficient_attention=False):
+        super().__init__()
+        inner_dim = dim_head * heads
+        self.scale = dim_head ** -0.5
+        self.heads = heads
+        self.dim_head = dim_head
+        self.efficient_attention = efficient_attention
+        self.to_q = nn.Linear(query_dim, inner_dim, bias=False)
+        self.to_k = nn.Linear(query_dim, inner_dim, bias=False)
+        self.to_v = nn.Linear(query_dim, inner_dim, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Dropout(dropout))
+
+    def _pack(self):
+        wq, wk, wv = w16(self.to_q.weight), w16(self.to_k.weight), w16(self.to_v.weight)
+        return {
+            "wqkv": torch.cat([wq, wk, wv], 0).contiguous(),
+            "wkv": torch.cat([wk, wv], 0).contiguous(),
+            "wo": w16(self.to_out[0].weight),
+            "bo": f32(self.to_out[0].bias),
+        }
+
+    def project_kv(self, x16: torch.Tensor) -> torch.Tensor:
+        return ops.gemm(x16, self.pk()["wkv"])
+
+    def _fwd(self, x16, B, N, residual=None, gate=1.0, extra_kv=None, n_extra=0, extra_batch=0, out=None):
+        """x16: normalised tokens [B*N, C].  extra_kv: [Be*n_extra, 2C] additional keys/values
+        (the object tokens of the gated block)."""
+        p = self.pk()
+        C = self.heads * self.dim_head
+        qkv = ops.gemm(x16, p["wqkv"])
+        kw = {}
+        if extra_kv is not None:
+            kw = dict(k1=extra_kv[:, :C], v1=extra_kv[:, C:2 * C], n1=n_extra, kv1_batch=extra_batch)
+        a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], batch=B, heads=self.heads,
+                          head_dim=self.dim_head, nq=N, n0=N, scale=self.scale, **kw)
+        return ops.gemm(a, p["wo"], p["bo"], residual=residual, gate=gate, out=out)
+
+    def forward(self, x, grounding_input=None, drop_box_mask=False):
+        x16, B, N = to_tokens(x)
+        return self._fwd(x16, B, N).view(B, N, -1).to(x.dtype)
+
+
+class GatedSelfAttentionDense(PackedModule):
+    """attention.py:285-311, restructured (exact in real arithmetic):
+    LayerNorm is per token, so norm1(cat[x, objs']) = cat[norm1 x, norm1 objs']; queries, the
+    out-projection and the softmax rows are computed only for the N visual tokens (the only rows
+    the reference keeps, :308) while the 184 object rows contribute keys/values -- computed once
+    per sample by `project_objs` and reused for all steps."""
+
+    def __init__(self, query_dim, context_dim, n_heads, d_head, efficient_attention=False):
+        super().__init__()
+        self.linear = nn.Linear(context_dim, query_dim)
+        self.attn = SelfAttention(query_dim=query_dim, heads=n_heads, dim_head=d_head,
+                                  efficient_attention=efficient_attention)
+        self.ff = FeedForward(query_dim, glu=True)
+        self.norm1 = nn.LayerNorm(query_dim)
+        self.norm2 = nn.LayerNorm(query_dim)
+        self.register_parameter('alpha_attn', nn.Parameter(torch.tensor(0.)))
+        self.register_parameter('alpha_dense', nn.Parameter(torch.tensor(0.)))
+        # set per step by utils.model.set_alpha_scale (1 for the first alpha*S steps, then 0)
+        self.scale = 1
+
+    def _pack(self):
+        return {
+            "wl": w16(self.linear.weight), "bl": f32(self.linear.bias),
+            "g1": f32(self.norm1.weight), "b1": f32(self.norm1.bias),
+            "g2": f32(self.norm2.weight), "b2": f32(self.norm2.bias),
+            "tanh_attn": math.tanh(float(self.alpha_attn.detach().float().cpu())),
+            "tanh_dense": math.tanh(float(self.alpha_dense.detach().float().cpu())),
+        }
+
+    def project_objs(self, objs16: torch.Tensor) -> torch.Tensor:
+        """objs16 fp16 [Bo*184, context_dim] -> K|V rows [Bo*184, 2C] = [Wk;Wv] norm1(linear(objs))."""
+        p = self.pk()
+        o = ops.gemm(objs16, p["wl"], p["bl"])
+        o = ops.layernorm(o, p["g1"], p["b1"], self.norm1.eps)
+        return self.attn.project_kv(o)
+
+    def _fwd(self, x16, B, N, obj_kv, n_obj, obj_batch):
+        """In-place on x16 (the residual stream).  Identity when scale == 0 (the alpha=0 steps)."""
+        if self.scale == 0:
+            return x16
+        p = self.pk()
+        n = ops.layernorm(x16, p["g1"], p["b1"], self.norm1.eps)
+        x16 = self.attn._fwd(n, B, N, residual=x16, gate=float(self.scale) * p["tanh_attn"],
+                             extra_kv=obj_kv, n_extra=n_obj, extra_batch=obj_batch, out=x16)
+        n = ops.layernorm(x16, p["g2"], p["b2"], self.norm2.eps)
+        return self.ff._fwd(n, residual=x16, gate=float(self.scale) * p["tanh_dense"], out=x16)
+
+    def forward(self, x, objs, grounding_input=None, drop_box_mask=False):
+        x16, B, N = to_tokens(x)
+        o16, Bo, n_obj = to_tokens(objs)
+        y = self._fwd(x16.clone(), B, N, self.project_objs(o16), n_obj, Bo)
+        return y.view(B, N, -1).to(x.dtype)
+
+
+class BasicTransformerBlock(PackedModule):
+    """attention.py:314-338: x = attn1(LN x)+x; x = fuser(x, objs); x = attn2(LN x, ctx)+x;
+    x = ff(LN x)+x.  All residual adds are GEMM epilogues writing the stream in place."""
+
+    def __init__(self, query_dim, key_dim, value_dim, n_heads, d_head, fuser_type, use_checkpoint=True,
+                 efficient_attention=False):
+        super().__init__()
+        self.attn1 = SelfAttention(query_dim=query_dim, heads=n_heads, dim_head=d_head,
+                                   efficient_attention=efficient_attention)
+        self.ff = FeedForward(query_dim, glu=True)
+        self.attn2 = CrossAttention(query_dim=query_dim, key_dim=key_dim, value_dim=value_dim, heads=n_heads,
+                                    dim_head=d_head, efficient_attention=efficient_attention)
+        self.norm1 = nn.LayerNorm(query_dim)
+        self.norm2 = nn.LayerNorm(query_dim)
+        self.norm3 = nn.LayerNorm(query_dim)
+        self.use_checkpoint = use_checkpoint
+        self.fuser = GatedSelfAttentionDense(query_dim, key_dim, n_heads, d_head,
+                                             efficient_attention=efficient_attention)
+
+    def _pack(self):
+        return {
+            "g1": f32(self.norm1.weight), "b1": f32(self.norm1.bias),
+            "g2": f32(self.norm2.weight), "b2": f32(self.norm2.bias),
+            "g3": f32(self.norm3.weight), "b3": f32(self.norm3.bias),
+        }
+
+    def _fwd(self, x16, B, N, ctx_kv, M, obj_kv, n_obj, obj_batch):
+        p = self.pk()
+        n = ops.layernorm(x16, p["g1"], p["b1"], self.norm1.eps)
+        x16 = self.attn1._fwd(n, B, N, residual=x16, out=x16)
+        x16 = self.fuser._fwd(x16, B, N, obj_kv, n_obj, obj_batch)
+        n = ops.layernorm(x16, p["g2"], p["b2"], self.norm2.eps)
+        x16 = self.attn2._fwd(n, ctx_kv, B, N, M, residual=x16, out=x16)
+        n = ops.layernorm(x16, p["g3"], p["b3"], self.norm3.eps)
+        return self.ff._fwd(n, residual=x16, out=x16)
+
+    def forward(self, x, context, objs, grounding_input=None, drop_box_mask=False):
+        return self._forward(x, context, objs, grounding_input, drop_box_mask=drop_box_mask)
+
+    def _forward(self, x, context, objs, grounding_input=None, drop_box_mask=False):
+        x16, B, N = to_tokens(x)
+        c16, _, M = to_tokens(context)
+        o16, Bo, n_obj = to_tokens(objs)
+        obj_kv = self.fuser.project_objs(o16) if self.fuser.scale != 0 else None
+        y = self._fwd(x16.clone(), B, N, self.attn2.project_kv(c16), M, obj_kv, n_obj, Bo)
+        return y.view(B, N, -1).to(x.dtype)
+
+
+def Normalize(in_channels):
+    return torch.nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
+
+
+class SpatialTransformer(PackedModule):
+    """attention.py:341-379: GroupNorm(eps 1e-6) -> 1x1 conv -> blocks -> 1x1 conv -> + x_in.
+    With NHWC activations the two rearranges are no-ops and the 1x1 convs are plain GEMMs; the
+    final residual is the proj_out GEMM's epilogue."""
+
+    def __init__(self, in_channels, key_dim, value_dim, n_heads, d_head, depth=1, fuser_type=None,
+                 use_checkpoint=True, efficient_attention=False):
+        super().__init__()
+        self.in_channels = in_channels
+        query_dim = n_heads * d_head
+        self.norm = Normalize(in_channels)
+        self.proj_in = nn.Conv2d(in_channels, query_dim, kernel_size=1, stride=1, padding=0)
+        self.transformer_blocks = nn.ModuleList([
+            BasicTransformerBlock(query_dim, key_dim, value_dim, n_heads, d_head, fuser_type,
+                                  use_checkpoint=use_checkpoint, efficient_attention=efficient_attention)
+            for _ in range(depth)])
+        self.proj_out = zero_module(nn.Conv2d(query_dim, in_channels, kernel_size=1, stride=1, padding=0))
+
+    def _pack(self):
+        return {
+            "gn_g": f32(self.norm.weight), "gn_b": f32(self.norm.bias),
+            "w_in": pack_conv1x1(w16(self.proj_in.weight)), "b_in": f32(self.proj_in.bias),
+            "w_out": pack_conv1x1(w16(self.proj_out.weight)), "b_out": f32(self.proj_out.bias),
+        }
+
+    def _fwd(self, x16, B, H, W, ctx_kvs, M, obj_kvs, n_obj, obj_batch):
+        """x16 fp16 [B*H*W, C].  ctx_kvs / obj_kvs: one entry per transformer block."""
+        p = self.pk()
+        n = ops.groupnorm(x16, p["gn_g"], p["gn_b"], batch=B, hw=H * W, groups=32, eps=self.norm.eps, silu=False)
+        t = ops.gemm(n, p["w_in"], p["b_in"])
+        for i, blk in enumerate(self.transformer_blocks):
+            t = blk._fwd(t, B, H * W, ctx_kvs[i], M, obj_kvs[i] if obj_kvs is not None else None, n_obj, obj_batch)
+        return ops.gemm(t, p["w_out"], p["b_out"], residual=x16)
+
+    def forward(self, x, context, objs, grounding_input=None, drop_box_mask=False):
+        x16, B, H, W = nchw_to_nhwc16(x)
+        c16, _, M = to_tokens(context)
+        o16, Bo, n_obj = to_tokens(objs)
+        ctx_kvs = [blk.attn2.project_kv(c16) for blk in self.transformer_blocks]
+        obj_kvs = [blk.fuser.project_objs(o16) if blk.fuser.scale != 0 else None for blk in self.transformer_blocks]
+        y = self._fwd(x16, B, H, W, ctx_kvs, M, obj_kvs, n_obj, Bo)
+        return nhwc16_to_nchw(y, B, H, W, x.dtype)

@@ -82,6 +82,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     args.bias = _ptr(bias)
     if rowadd is not None:
         _req(rowadd, HALF, "rowadd")
+        args.ldra = rowadd.stride(0)
     args.rowadd = _ptr(rowadd)
     if residual is not None:
         _req(residual, HALF, "residual")
@@ -262,4 +263,13 @@ def latent_mean(xs, out: torch.Tensor) -> torch.Tensor:
     ptrs = torch.tensor([t.data_ptr() for t in xs], dtype=torch.int64).to(out.device)
     check(lib.idiff_latent_mean(ptrs.data_ptr(), len(xs), out.data_ptr(), out.numel(), _stream()),
           "idiff_latent_mean")
+    return out
+
+
+def silu(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x, HALF, "x")
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    check(lib.idiff_silu_f16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "idiff_silu_f16")
     return out
