@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec/GPU of the InstanceDiffusion sampling hot path on B200.
+
+Workload (BASELINE.json configs[1]): batch=4 images of 512x512 (latent 64x64), 8 box instances
+each, 50-step PLMS, classifier-free guidance 7.5, alpha schedule [0.8, 0, 0.2], fp16 compute.
+One "step" of the bench contract = one full `sampler.sample(...)` call over one batch (latent out);
+timed region = the sampler only (no CLIP, no VAE), as SURVEY.md section 8d prescribes.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--mis 0.0] [--impl reference]
+
+N > 1: launched under torch.distributed.run, one rank per GPU; rank 0's synthetic weights are
+broadcast once over NCCL, every rank then samples its own batch of prompts (weak scaling, no
+per-step collective).  `value` = images of all ranks / max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from functools import partial
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "config2: batch=4 512x512, 8 box instances, 50-step PLMS, CFG 7.5, fp16, 1 GPU"
+BATCH, N_INST, S_STEPS, GUIDANCE, ALPHA_TYPE = 4, 8, 50, 7.5, [0.8, 0.0, 0.2]
+
+
+def forwards_per_sample_call(S, n, mis):
+    """UNet forwards per `sample()` call, each at batch B."""
+    ms = int(S * mis)
+    return 2 * ((n + 1) * (ms + 1) + (S - ms)) if mis > 0 else 2 * (S + 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe) during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx = max(mx, float(s[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the plain-torch restatement of the reference path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_forward_seconds(n_forwards: int = 2, threads: int | None = None):
+    """Times `n_forwards` steady-state UNet forwards (B=1, 512^2, fp32) of oracle/torch_oracle.py --
+    the CPU restatement of the reference's forward_single_input -- after one untimed call."""
+    from oracle import torch_oracle as TO
+    from instancediffusion_b200 import synthetic
+    from instancediffusion_b200.weights import UNIFUSION_FLAGS, synth_tensor, unet_config
+    from instancediffusion_b200.ldm.modules.diffusionmodules.openaimodel import UNetModel
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    with torch.device("meta"):
+        m = UNetModel(**unet_config("box"))
+    sd = {k: synth_tensor(k, tuple(v.shape), 0) for k, v in m.state_dict().items() if "convnext" not in k}
+    gb = synthetic.make_grounding_batch(1, N_INST, 3, "box")
+    gi = dict(boxes=gb["boxes"], masks=gb["masks"], positive_embeddings=gb["text_embeddings"],
+              scribbles=gb["scribbles"], polygons=gb["polygons"], segs=gb["segs"], points=gb["points"])
+    x = synthetic.make_noise(1, 3)
+    ctx = synthetic.make_context(1, 4)
+    t = torch.full((1,), 601, dtype=torch.long)
+    flags = UNIFUSION_FLAGS["box"]
+    with torch.no_grad():
+        TO.unet_forward(sd, x, t, ctx, gi, flags)
+        t0 = time.perf_counter()
+        for _ in range(n_forwards):
+            TO.unet_forward(sd, x, t, ctx, gi, flags)
+        dt = (time.perf_counter() - t0) / n_forwards
+    return dt, threads
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path (the oracle port of its
+    forward; the Python reference itself cannot travel to the GPU box), all host threads.  Each
+    step is a bounded sample: `fw` steady-state forwards at B=1, extrapolated to the forward count
+    of the workload (BASELINE.md section 4 'extrapolated')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fpc = forwards_per_sample_call(S_STEPS, N_INST, args.mis)
+    times = []
+    threads = os.cpu_count()
+    for i in range(args.warmup + args.steps):
+        dt, threads = cpu_forward_seconds(1, threads)
+        if i >= args.warmup:
+            times.append(dt)
+    t_fwd = sum(times) / len(times)
+    # one sample() call of B images = fpc forwards at batch B; CPU time scales ~linearly in batch
+    sec_per_image = fpc * t_fwd
+    value = 1.0 / sec_per_image
+    line = {
+        "impl": "reference", "metric": "images/sec/GPU @512^2 fp16 50-step PLMS, 8 instances", "value": value,
+        "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": BATCH * sec_per_image * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "mis": args.mis, "forwards_per_call": fpc},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{len(times)} steady-state UNet forwards at B=1 (fp32, {threads} threads), "
+                                   f"{t_fwd:.2f} s each, x{fpc} forwards per image (extrapolated)"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ------------------------------------------------------------------------------------------------
+def build_pipeline(device, rank, world):
+    from instancediffusion_b200 import parallel
+    from instancediffusion_b200.ldm.models.diffusion.ldm import LatentDiffusion
+    from instancediffusion_b200.weights import build_unet
+    # rank 0 materialises the synthetic weights; the other ranks receive them over NCCL
+    model = build_unet("box", device, seed=0 if rank == 0 else None)
+    sent = parallel.broadcast_module_(model, src=0)
+    diffusion = LatentDiffusion(linear_start=0.00085, linear_end=0.012, timesteps=1000).to(device)
+    # SD1.5 first conv swapped in at alpha == 0 (openaimodel.py:469-480).  The shipped 48 KB file is
+    # a fixture under tests/golden/; a synthetic stand-in of the same shape is used if it is absent.
+    p = os.path.join(ROOT, "tests", "golden", "sd15_first_conv.pt")
+    if os.path.exists(p):
+        sd_conv = torch.load(p, map_location="cpu")
+    else:
+        g = torch.Generator().manual_seed(5)
+        sd_conv = {"weight": torch.randn((320, 4, 3, 3), generator=g) * 0.1, "bias": torch.zeros(320)}
+    model.restore_first_conv_from_SD = lambda: (None if getattr(model, "_first_conv_restored", False)
+                                                else model.set_sd_first_conv(sd_conv))
+    return model, diffusion, sent
+
+
+def make_sampler(model, diffusion, mis):
+    from instancediffusion_b200.ldm.models.diffusion.plms import PLMSSampler
+    from instancediffusion_b200.ldm.models.diffusion.plms_instance import PLMSSamplerInst
+    from instancediffusion_b200.utils.model import alpha_generator, set_alpha_scale
+    agen = partial(alpha_generator, type=ALPHA_TYPE)
+    if mis > 0:
+        return PLMSSamplerInst(diffusion, model, alpha_generator_func=agen, set_alpha_scale=set_alpha_scale, mis=mis)
+    return PLMSSampler(diffusion, model, alpha_generator_func=agen, set_alpha_scale=set_alpha_scale)
+
+
+def host_inputs(model, seed, mis):
+    """Pinned host copies of everything `sample()` consumes for one batch (the e2e leg copies them
+    to the device inside the timed region)."""
+    from instancediffusion_b200 import synthetic
+    gti = model.grounding_tokenizer_input
+    inputs, uc = synthetic.make_sampler_inputs(gti, BATCH, N_INST, seed, "box", mis=mis > 0, device="cpu")
+    lst = inputs if isinstance(inputs, list) else [inputs]
+
+    def pin(t):
+        if t.dim() == 4 and t.stride(-1) == 0:  # zero `segs` view: stays a broadcast view
+            return t
+        return t.contiguous().pin_memory()
+
+    host = []
+    for inp in lst:
+        gi = {k: pin(v) for k, v in inp["grounding_input"].items()}
+        host.append(dict(x=pin(inp["x"]), context=pin(inp["context"]), grounding_input=gi))
+    return host, pin(uc), isinstance(inputs, list)
+
+
+def to_device(host, uc, is_list, device, gti):
+    nbytes = 0
+    dev = []
+    for h in host:
+        gi = {}
+        for k, v in h["grounding_input"].items():
+            if v.dim() == 4 and v.stride(-1) == 0:
+                gi[k] = torch.zeros((v.shape[0], v.shape[1], 1, 1), device=device).expand(*v.shape)
+            else:
+                gi[k] = v.to(device, non_blocking=True)
+                nbytes += v.numel() * v.element_size()
+        x = h["x"].to(device, non_blocking=True)
+        c = h["context"].to(device, non_blocking=True)
+        nbytes += x.numel() * 4 + c.numel() * 4
+        gti.prepare({**gi, "text_embeddings": gi["positive_embeddings"]})
+        dev.append(dict(x=x, timesteps=None, context=c, grounding_input=gi))
+    ucd = uc.to(device, non_blocking=True)
+    nbytes += uc.numel() * 4
+    return (dev if is_list else dev[0]), ucd, nbytes
+
+
+def roofline_pass(model, device, peaks):
+    """One eager (graph-free) batched cond+uncond forward at the bench batch with every launch
+    bracketed by CUDA events on the launching stream: per-kernel-class time, algorithmic FLOPs /
+    bytes, and the roofline of the dominant class."""
+    from instancediffusion_b200 import ops, synthetic
+    from instancediffusion_b200.utils.model import set_alpha_scale
+    gti = model.grounding_tokenizer_input
+    inp, uc = synthetic.make_sampler_inputs(gti, BATCH, N_INST, 77, "box", mis=False, device=device)
+    inp["timesteps"] = torch.full((BATCH,), 601, dtype=torch.long, device=device)
+    un = dict(x=inp["x"], timesteps=inp["timesteps"], context=uc)
+    set_alpha_scale(model, 1)
+    saved = model.use_cuda_graph
+    model.use_cuda_graph = False
+    model.forward_batched([inp, un])  # warm: hoisted tensors cached
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    agg = {}
+    for _ in range(3):
+        flush.zero_()  # > L2 (126 MB) written between iterations
+        ops.PROFILE = []
+        model.forward_batched([inp, un])
+        torch.cuda.synchronize()
+        for kind, fl, by, s, e in ops.PROFILE:
+            a = agg.setdefault(kind, [0.0, 0.0, 0.0, 0])
+            a[0] += s.elapsed_time(e) * 1e-3
+            a[1] += fl
+            a[2] += by
+            a[3] += 1
+        ops.PROFILE = None
+    model.use_cuda_graph = saved
+    tot = sum(a[0] for a in agg.values())
+    breakdown = {k: {"share": a[0] / tot, "launches": a[3] // 3, "ms": a[0] / 3 * 1e3,
+                     "tflops": (a[1] / a[0] / 1e12) if a[1] else None,
+                     "gbs": a[2] / a[0] / 1e9} for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+    dom = max(agg.items(), key=lambda kv: kv[1][0])
+    kind, a = dom
+    if a[1] > 0:
+        achieved = a[1] / a[0] / 1e12
+        peak = peaks.get("bf16_tflops_sustained") or 1400.0
+        roof = {"bound": "tensor", "kernel": kind, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"}
+    else:
+        achieved = a[2] / a[0] / 1e9
+        peak = peaks.get("hbm_gbs") or 6650.0
+        roof = {"bound": "hbm", "kernel": kind, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"}
+    n_launch = sum(a[3] for a in agg.values()) // 3
+    return roof, breakdown, n_launch
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--mis", type=float, default=0.0, help="Multi-instance Sampler fraction (inference.py default 0.36)")
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    from instancediffusion_b200 import _lib, parallel
+    from instancediffusion_b200.utils.model import set_alpha_scale
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the CUDA arm has no CPU fallback (use --impl reference)")
+    _lib.load()
+    rank, local_rank, world = parallel.init_distributed()
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    model, diffusion, sent = build_pipeline(device, rank, world)
+    sampler = make_sampler(model, diffusion, args.mis)
+    gti = model.grounding_tokenizer_input
+    host, uc_host, is_list = host_inputs(model, 1000 + rank, args.mis)
+    shape = (BATCH, 4, 64, 64)
+    fpc = forwards_per_sample_call(S_STEPS, N_INST, args.mis)
+
+    def reset():
+        # every sample() call starts from a fresh model state and recomputes the per-sample hoisted
+        # tensors (UniFusion tokens, object / text K/V): nothing is carried over between timed steps
+        model.undo_first_conv_restore()
+        set_alpha_scale(model, 1)
+        model._ctx_cache.clear()
+        model._obj_cache.clear()
+
+    def run_resident(inputs, uc):
+        # fresh trajectory state; the latent x is cloned so every step starts from the same noise
+        if isinstance(inputs, list):
+            ins = [dict(i, x=i["x"].clone()) for i in inputs]
+        else:
+            ins = dict(inputs, x=inputs["x"].clone())
+        return sampler.sample(S=S_STEPS, shape=shape, input=ins, uc=uc, guidance_scale=GUIDANCE)
+
+    # ---- device-resident leg -------------------------------------------------------------------
+    dev_inputs, uc_dev, h2d_bytes = to_device(host, uc_host, is_list, device, gti)
+    torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        reset()
+        run_resident(dev_inputs, uc_dev)
+    torch.cuda.synchronize()
+    parallel.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    with ClockSampler(local_rank) as clk:
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(args.steps):
+            reset()
+            out = run_resident(dev_inputs, uc_dev)
+        ev[1].record()
+        torch.cuda.synchronize()
+    parallel.barrier()
+    t_dev = parallel.max_over_ranks(ev[0].elapsed_time(ev[1]) * 1e-3, device)
+    assert torch.isfinite(out).all()
+
+    # ---- end-to-end leg: host buffers in, latent back on the host, every step ------------------
+    result_host = torch.empty(shape, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev2[0].record()
+    for _ in range(args.steps):
+        reset()
+        di, ud, _ = to_device(host, uc_host, is_list, device, gti)
+        o = sampler.sample(S=S_STEPS, shape=shape, input=di, uc=ud, guidance_scale=GUIDANCE)
+        result_host.copy_(o, non_blocking=True)
+    ev2[1].record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    t_e2e = parallel.max_over_ranks(ev2[0].elapsed_time(ev2[1]) * 1e-3, device)
+
+    images = BATCH * args.steps * world
+    value = images / t_dev
+    e2e_value = images / t_e2e
+    if rank != 0:
+        return
+    roof, breakdown, launches_per_fwd = roofline_pass(model, device, peaks)
+    flop_per_image = None
+    ms_step = t_dev / args.steps * 1e3
+    line = {
+        "metric": "images/sec/GPU @512^2 fp16 50-step PLMS, 8 instances", "value": value, "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "mis": args.mis, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                   "forwards_per_call": fpc, "forward_batch": 2 * BATCH,
+                   "l2_policy": "activations per forward (>1 GB at batch 8) exceed the 126 MB L2; roofline pass "
+                                "flushes L2 (256 MB write) between iterations",
+                   "cuda_graph": bool(model.use_cuda_graph), "weights": "seeded random (no checkpoint offline)",
+                   "weight_broadcast_bytes": sent},
+        "per_gpu_images_per_s": value / world,
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": result_host.numel() * 4},
+        "gpu_launches": int(launches_per_fwd * (fpc // 2) * args.steps),
+        "roofline": roof,
+        "breakdown": breakdown,
+    }
+    # per-image algorithmic work: F_min(alpha=1)=1136, F_min(alpha=0)=803 GFLOP/forward/sample
+    if args.mis == 0:
+        tflop = (2 * 41 * 1.136 + 2 * 10 * 0.803)
+        peak = peaks.get("bf16_tflops_sustained") or 1400.0
+        line["model_roofline"] = {"tflop_per_image_fmin": tflop, "achieved_tflops": value / world * tflop,
+                                  "frac_of_sustained_peak": value / world * tflop / peak}
+    if not args.no_cpu_baseline:
+        try:
+            dt, threads = cpu_forward_seconds(2)
+            line["cpu_baseline"] = {
+                "value": 1.0 / (fpc * dt), "unit": "images/s", "cores": threads, "kind": "port",
+                "sample": f"2 steady-state UNet forwards at B=1 of oracle/torch_oracle.py (fp32, {threads} threads), "
+                          f"{dt:.2f} s each, x{fpc} forwards per image (extrapolated)"}
+        except Exception as exc:  # the baseline must never take the bench line down
+            line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {exc!r}"}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,24 @@ from ._lib import AttnArgs, GemmArgs, check
 HALF = torch.float16
 
 
+# Optional per-launch timing (bench.py's roofline pass): when PROFILE is a list, every wrapper
+# brackets its launch with CUDA events on the launching stream and appends
+# (kind, algorithmic_flops, algorithmic_bytes, start_event, end_event).
+PROFILE = None
+
+
+def _launch(kind: str, flops: float, nbytes: float, fn):
+    if PROFILE is None:
+        return fn()
+    s = torch.cuda.Event(enable_timing=True)
+    e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = fn()
+    e.record()
+    PROFILE.append((kind, flops, nbytes, s, e))
+    return rc
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -95,7 +113,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     args.flags = flags
     if conv is not None:
         args.conv_b, args.conv_h, args.conv_w, args.conv_cin = conv
-    check(lib.idiff_gemm(C.byref(args), _stream()), "idiff_gemm")
+    kind = "conv3x3" if conv is not None else ("gemm_geglu" if geglu else "gemm")
+    nbytes = 2.0 * (M * K / (9 if conv is not None else 1) + N * K + M * n_out)
+    check(_launch(kind, 2.0 * M * N * K, nbytes, lambda: lib.idiff_gemm(C.byref(args), _stream())), "idiff_gemm")
     return result
 
 
@@ -125,7 +145,10 @@ def attention(q: torch.Tensor, k0: torch.Tensor, v0: torch.Tensor, *, batch: int
     a.nq, a.n0, a.n1 = nq, n0, n1
     a.kv1_batch = kv1_batch if kv1_batch else batch
     a.scale = float(scale)
-    check(lib.idiff_attention(C.byref(a), _stream()), "idiff_attention")
+    flops = 4.0 * batch * heads * nq * (n0 + n1) * head_dim
+    nbytes = 2.0 * batch * C_ * (2 * nq + 2 * (n0 + n1))
+    check(_launch(f"attention_d{head_dim}", flops, nbytes, lambda: lib.idiff_attention(C.byref(a), _stream())),
+          "idiff_attention")
     return out
 
 
@@ -139,9 +162,9 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, batch
         out = torch.empty_like(x)
     if stats_ws is None:
         stats_ws = torch.empty(batch * groups * 2, dtype=torch.float32, device=x.device)
-    check(lib.idiff_groupnorm(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                              stats_ws.data_ptr(), batch, hw, Cc, groups, eps, int(silu), _stream()),
-          "idiff_groupnorm")
+    check(_launch("groupnorm", 0.0, 4.0 * x.numel(), lambda: lib.idiff_groupnorm(
+        x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats_ws.data_ptr(), batch, hw, Cc,
+        groups, eps, int(silu), _stream())), "idiff_groupnorm")
     return out
 
 
@@ -154,8 +177,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         raise _lib.IdiffError("layernorm input must be contiguous")
     if out is None:
         out = torch.empty_like(x2)
-    check(lib.idiff_layernorm(x2.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                              x2.shape[0], x2.shape[1], eps, _stream()), "idiff_layernorm")
+    check(_launch("layernorm", 0.0, 4.0 * x2.numel(), lambda: lib.idiff_layernorm(
+        x2.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), x2.shape[0], x2.shape[1], eps,
+        _stream())), "idiff_layernorm")
     return out
 
 
@@ -170,9 +194,9 @@ def scaleu_concat(h: torch.Tensor, skip: torch.Tensor, b1: torch.Tensor, s: floa
         out = torch.empty((batch * height * width, c1 + c2), dtype=HALF, device=h.device)
     if coef_ws is None:
         coef_ws = torch.empty(batch * c2 * 8, dtype=torch.float32, device=h.device)
-    check(lib.idiff_scaleu_concat(h.data_ptr(), skip.data_ptr(), out.data_ptr(), b1.data_ptr(), float(s),
-                                  coef_ws.data_ptr(), batch, height, width, c1, c2, _stream()),
-          "idiff_scaleu_concat")
+    check(_launch("scaleu_concat", 0.0, 4.0 * (h.numel() + skip.numel()), lambda: lib.idiff_scaleu_concat(
+        h.data_ptr(), skip.data_ptr(), out.data_ptr(), b1.data_ptr(), float(s), coef_ws.data_ptr(), batch, height,
+        width, c1, c2, _stream())), "idiff_scaleu_concat")
     return out
 
 

@@ -1,0 +1,158 @@
+"""TEST INFRASTRUCTURE -- generate the golden fixtures under tests/golden/ by running the
+reference's own, unmodified modules (imported from $IDIFF_REF, default /root/reference) on the CPU
+in fp32 over the seeded cases of tests/cases.py.  Run in the authoring container:
+
+    python oracle/make_golden.py [--only modules,unifusion,fourier,unet,samplers]
+
+The fixtures are the parity pin that travels to the GPU box (where the reference does not exist).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import sys
+import time
+from functools import partial
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+import cases  # noqa: E402
+from oracle import ref_harness, torch_oracle  # noqa: E402
+from instancediffusion_b200 import synthetic  # noqa: E402
+from instancediffusion_b200.weights import UNIFUSION_FLAGS, load_synthetic  # noqa: E402
+
+
+def ref_class(ref, path: str):
+    mod, cls = path.split(":")
+    return getattr(importlib.import_module("ldm.modules." + mod), cls)
+
+
+def gen_modules(ref):
+    out = {}
+    for name, spec in cases.MODULE_CASES.items():
+        t = time.time()
+        out[name] = cases.run_module_case(name, spec, ref_class(ref, spec["module"])).float().contiguous()
+        print(f"  {name}: {tuple(out[name].shape)} absmax={out[name].abs().max():.3f} ({time.time() - t:.1f}s)")
+    torch.save(out, os.path.join(GOLDEN, "modules.pt"))
+
+
+def gen_fourier(ref):
+    out = {}
+    for name, spec in cases.FOURIER_CASES.items():
+        x = cases.synth_input(name, "x", spec["shape"]) + 0.5
+        out[name] = ref.openaimodel.Fourier_filter(x, threshold=1, scale=spec["scale"]).float().contiguous()
+        print(f"  {name}: {tuple(out[name].shape)}")
+    t = torch.tensor([981, 1, 501, 21])
+    out["timestep_embedding"] = ref.util.timestep_embedding(t, 320, repeat_only=False).float()
+    torch.save(out, os.path.join(GOLDEN, "fourier.pt"))
+
+
+def gen_unifusion(ref):
+    out = {}
+    for name, spec in cases.UNIFUSION_CASES.items():
+        flags = UNIFUSION_FLAGS[spec["flavor"]]
+        with ref_harness.fast_init():
+            net = ref.text_grounding_net.UniFusion(in_dim=768, out_dim=768, mid_dim=3072, **flags).eval()
+        load_synthetic(net, 0, prefix="position_net.")
+        gb = synthetic.make_grounding_batch(spec["batch"], spec["n"], spec["seed"], spec["flavor"])
+        gi = ref.GroundingNetInput().prepare(gb)
+        with torch.no_grad():
+            objs, dbm = net(gi["boxes"], gi["masks"], gi["positive_embeddings"], gi["scribbles"], gi["polygons"],
+                            gi["segs"], gi["points"])
+        out[name] = objs.float().contiguous()
+        out[name + "/drop_box_mask"] = torch.tensor(int(dbm))
+        print(f"  {name}: {tuple(objs.shape)} drop_box_mask={dbm} absmax={objs.abs().max():.3f}")
+    torch.save(out, os.path.join(GOLDEN, "unifusion.pt"))
+
+
+def gen_unet_and_samplers(ref, do_unet=True, do_samplers=True):
+    spec = cases.UNET_CASE
+    t0 = time.time()
+    model = ref_harness.build_ref_unet(ref, spec["flavor"], spec["weight_seed"])
+    print(f"  reference UNet built in {time.time() - t0:.1f}s")
+    # schema (names + shapes) for the CPU-side state_dict compatibility test
+    schema = {k: list(v.shape) for k, v in model.state_dict().items()}
+    with open(os.path.join(GOLDEN, "unet_schema.json"), "w") as fh:
+        json.dump(schema, fh)
+    # the SD1.5 first-conv tensors the reference swaps in at alpha == 0 (data, 48 KB)
+    sd_conv = torch.load(os.path.join(ref.root, "pretrained", "SD_v1_5_input_conv_weight_bias.pth"), map_location="cpu")
+    torch.save({k: v.float().clone() for k, v in sd_conv.items()}, os.path.join(GOLDEN, "sd15_first_conv.pt"))
+
+    gti = model.grounding_tokenizer_input
+    diffusion = ref.LatentDiffusion(linear_start=0.00085, linear_end=0.012, timesteps=1000)
+    setter = partial(ref_harness.set_alpha_scale, ref)
+
+    def fresh_first_conv():
+        if hasattr(model, "first_conv_state_dict"):
+            conv = torch.nn.Conv2d(4, 320, 3, padding=1)
+            conv.load_state_dict(model.first_conv_state_dict)
+            model.input_blocks[0][0] = conv
+
+    if do_unet:
+        out = {}
+        inp, uc = synthetic.make_sampler_inputs(gti, spec["batch"], spec["n"], spec["seed"], spec["flavor"], mis=False)
+        ts = torch.full((spec["batch"],), spec["t"], dtype=torch.long)
+        setter(model, 1)
+        with torch.no_grad():
+            t = time.time()
+            gi = inp["grounding_input"]
+            out["objs"], _ = model.position_net(gi["boxes"], gi["masks"], gi["positive_embeddings"], gi["scribbles"],
+                                                gi["polygons"], gi["segs"], gi["points"])
+            out["eps_cond"] = model(dict(x=inp["x"], timesteps=ts, context=inp["context"], grounding_input=gi))
+            print(f"  eps_cond {time.time() - t:.1f}s absmax={out['eps_cond'].abs().max():.3f}")
+            out["eps_null"] = model(dict(x=inp["x"], timesteps=ts, context=uc))
+            setter(model, 0)
+            model.restore_first_conv_from_SD()
+            out["eps_alpha0"] = model(dict(x=inp["x"], timesteps=ts, context=inp["context"], grounding_input=gi))
+            fresh_first_conv()
+            setter(model, 1)
+        torch.save({k: v.float().contiguous() for k, v in out.items()}, os.path.join(GOLDEN, "unet.pt"))
+
+    if do_samplers:
+        out = {}
+        for name, sc in cases.SAMPLER_CASES.items():
+            fresh_first_conv()
+            agen = partial(torch_oracle.alpha_schedule, alpha_type=sc["alpha_type"])
+            use_mis = sc["mis"] > 0
+            inputs, uc = synthetic.make_sampler_inputs(gti, sc["batch"], sc["n"], sc["seed"], "box", mis=use_mis)
+            if use_mis:
+                sampler = ref.PLMSSamplerInst(diffusion, model, alpha_generator_func=agen, set_alpha_scale=setter, mis=sc["mis"])
+            else:
+                sampler = ref.PLMSSampler(diffusion, model, alpha_generator_func=agen, set_alpha_scale=setter)
+            t = time.time()
+            shape = (sc["batch"], 4, 64, 64)
+            x = sampler.sample(S=sc["S"], shape=shape, input=inputs, uc=uc, guidance_scale=sc["guidance"])
+            out[name] = x.float().contiguous()
+            print(f"  sampler {name}: {time.time() - t:.1f}s absmax={x.abs().max():.3f} finite={bool(torch.isfinite(x).all())}")
+        torch.save(out, os.path.join(GOLDEN, "samplers.pt"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="modules,fourier,unifusion,unet,samplers")
+    args = ap.parse_args()
+    only = set(args.only.split(","))
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(GOLDEN, exist_ok=True)
+    ref = ref_harness.import_reference()
+    print(f"reference at {ref.root}; torch {torch.__version__}; threads {torch.get_num_threads()}")
+    if "modules" in only:
+        print("module cases"); gen_modules(ref)
+    if "fourier" in only:
+        print("fourier / timestep cases"); gen_fourier(ref)
+    if "unifusion" in only:
+        print("unifusion cases"); gen_unifusion(ref)
+    if "unet" in only or "samplers" in only:
+        print("unet / sampler cases"); gen_unet_and_samplers(ref, "unet" in only, "samplers" in only)
+
+
+if __name__ == "__main__":
+    main()

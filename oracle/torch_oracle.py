@@ -1,0 +1,341 @@
+"""TEST INFRASTRUCTURE -- a plain-PyTorch fp32 restatement of the reference's sampling hot path,
+written functionally over a `state_dict` (no nn.Module, nothing imported from the reference, so it
+runs on the GPU box where /root/reference does not exist).  Each function cites the reference
+file:line it follows.  It is pinned against fixtures produced by the reference's own modules
+(oracle/make_golden.py -> tests/golden/*.pt, checked by tests/test_oracle_cpu.py).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline / `--impl reference` leg may
+import this file.  The product never does: instancediffusion_b200 has no CPU path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+HEADS = 8  # configs/test_*.yaml:19 num_heads
+
+
+# ------------------------------------------------------------------------------------------------
+# ldm/modules/attention.py
+# ------------------------------------------------------------------------------------------------
+def linear(sd: SD, p: str, x):
+    return F.linear(x, sd[p + ".weight"], sd.get(p + ".bias"))
+
+
+def feed_forward(sd: SD, p: str, x):
+    """FeedForward(glu=True), attention.py:36-63: Linear(C,8C) -> a*gelu(g) (erf) -> Linear(4C,C)."""
+    h = linear(sd, p + ".net.0.proj", x)
+    a, g = h.chunk(2, dim=-1)
+    return linear(sd, p + ".net.2", a * F.gelu(g))
+
+
+def _sdpa(q, k, v, heads):
+    """attention.py:130-144 / 183-185,257-267: head split, softmax(q k^T d^-1/2) v, head merge."""
+    B, N, C = q.shape
+    M = k.shape[1]
+    d = C // heads
+    q = q.view(B, N, heads, d).permute(0, 2, 1, 3)
+    k = k.view(B, M, heads, d).permute(0, 2, 1, 3)
+    v = v.view(B, M, heads, d).permute(0, 2, 1, 3)
+    att = torch.softmax((q @ k.transpose(-1, -2)) * (d ** -0.5), dim=-1)
+    return (att @ v).permute(0, 2, 1, 3).reshape(B, N, C)
+
+
+def self_attention(sd: SD, p: str, x, heads=HEADS):
+    """SelfAttention.forward, attention.py:174-282 (efficient path, no mask)."""
+    o = _sdpa(linear(sd, p + ".to_q", x), linear(sd, p + ".to_k", x), linear(sd, p + ".to_v", x), heads)
+    return linear(sd, p + ".to_out.0", o)
+
+
+def cross_attention(sd: SD, p: str, x, ctx, heads=HEADS):
+    """CrossAttention.forward, attention.py:120-157."""
+    o = _sdpa(linear(sd, p + ".to_q", x), linear(sd, p + ".to_k", ctx), linear(sd, p + ".to_v", ctx), heads)
+    return linear(sd, p + ".to_out.0", o)
+
+
+def layer_norm(sd: SD, p: str, x):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
+
+
+def gated_self_attention(sd: SD, p: str, x, objs, scale=1.0, heads=HEADS):
+    """GatedSelfAttentionDense.forward, attention.py:304-311 -- as written there: concatenate, norm,
+    attend over all N+184 rows, keep the first N."""
+    n_vis = x.shape[1]
+    o = linear(sd, p + ".linear", objs)
+    a = self_attention(sd, p + ".attn", layer_norm(sd, p + ".norm1", torch.cat([x, o], dim=1)), heads)
+    x = x + scale * torch.tanh(sd[p + ".alpha_attn"]) * a[:, :n_vis]
+    x = x + scale * torch.tanh(sd[p + ".alpha_dense"]) * feed_forward(sd, p + ".ff", layer_norm(sd, p + ".norm2", x))
+    return x
+
+
+def basic_transformer_block(sd: SD, p: str, x, ctx, objs, scale=1.0, heads=HEADS):
+    """BasicTransformerBlock._forward, attention.py:333-338."""
+    x = self_attention(sd, p + ".attn1", layer_norm(sd, p + ".norm1", x), heads) + x
+    x = gated_self_attention(sd, p + ".fuser", x, objs, scale, heads)
+    x = cross_attention(sd, p + ".attn2", layer_norm(sd, p + ".norm2", x), ctx, heads) + x
+    x = feed_forward(sd, p + ".ff", layer_norm(sd, p + ".norm3", x)) + x
+    return x
+
+
+def spatial_transformer(sd: SD, p: str, x, ctx, objs, scale=1.0, heads=HEADS):
+    """SpatialTransformer.forward, attention.py:366-379 (GroupNorm eps 1e-6, :75-76)."""
+    b, c, h, w = x.shape
+    x_in = x
+    x = F.group_norm(x, 32, sd[p + ".norm.weight"], sd[p + ".norm.bias"], 1e-6)
+    x = F.conv2d(x, sd[p + ".proj_in.weight"], sd[p + ".proj_in.bias"])
+    x = x.permute(0, 2, 3, 1).reshape(b, h * w, -1)
+    i = 0
+    while f"{p}.transformer_blocks.{i}.norm1.weight" in sd:
+        x = basic_transformer_block(sd, f"{p}.transformer_blocks.{i}", x, ctx, objs, scale, heads)
+        i += 1
+    x = x.reshape(b, h, w, -1).permute(0, 3, 1, 2)
+    x = F.conv2d(x, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
+    return x + x_in
+
+
+# ------------------------------------------------------------------------------------------------
+# ldm/modules/diffusionmodules/openaimodel.py
+# ------------------------------------------------------------------------------------------------
+def resblock(sd: SD, p: str, x, emb):
+    """ResBlock._forward, openaimodel.py:237-257 (no up/down, no scale-shift)."""
+    h = F.silu(F.group_norm(x.float(), 32, sd[p + ".in_layers.0.weight"], sd[p + ".in_layers.0.bias"], 1e-5))
+    h = F.conv2d(h, sd[p + ".in_layers.2.weight"], sd[p + ".in_layers.2.bias"], padding=1)
+    e = linear(sd, p + ".emb_layers.1", F.silu(emb))
+    h = h + e[:, :, None, None]
+    h = F.silu(F.group_norm(h, 32, sd[p + ".out_layers.0.weight"], sd[p + ".out_layers.0.bias"], 1e-5))
+    h = F.conv2d(h, sd[p + ".out_layers.3.weight"], sd[p + ".out_layers.3.bias"], padding=1)
+    if p + ".skip_connection.weight" in sd:
+        x = F.conv2d(x, sd[p + ".skip_connection.weight"], sd[p + ".skip_connection.bias"])
+    return x + h
+
+
+def upsample(sd: SD, p: str, x):
+    """Upsample.forward, openaimodel.py:100-110."""
+    x = F.interpolate(x, scale_factor=2, mode="nearest")
+    return F.conv2d(x, sd[p + ".conv.weight"], sd[p + ".conv.bias"], padding=1)
+
+
+def downsample(sd: SD, p: str, x):
+    """Downsample.forward, openaimodel.py:130-141 (stride 2, padding 1)."""
+    return F.conv2d(x, sd[p + ".op.weight"], sd[p + ".op.bias"], stride=2, padding=1)
+
+
+def fourier_filter(x, threshold, scale):
+    """Fourier_filter, openaimodel.py:25-48, as written there (FFT, centred mask, inverse, real part)."""
+    B, C, H, W = x.shape
+    xf = torch.fft.fftshift(torch.fft.fftn(x.float(), dim=(-2, -1)), dim=(-2, -1))
+    mask = torch.ones((B, C, H, W), device=x.device)
+    crow, ccol = H // 2, W // 2
+    mask[..., crow - threshold:crow + threshold, ccol - threshold:ccol + threshold] = scale
+    xf = torch.fft.ifftshift(xf * mask, dim=(-2, -1))
+    return torch.fft.ifftn(xf, dim=(-2, -1)).real.to(x.dtype)
+
+
+def timestep_embedding(t, dim, max_period=10000):
+    """util.py:160-180: [cos(t f) | sin(t f)], f_k = exp(-ln(max_period) k / half)."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# ldm/modules/diffusionmodules/text_grounding_net.py
+# ------------------------------------------------------------------------------------------------
+def fourier_embed(x, num_freqs=16, temperature=100):
+    """FourierEmbedder.__call__, util.py:19-26: cat_k [sin(f_k x), cos(f_k x)], f_k = T^(k/num)."""
+    freqs = temperature ** (torch.arange(num_freqs) / num_freqs)
+    out = []
+    for f in freqs:
+        out.append(torch.sin(f * x))
+        out.append(torch.cos(f * x))
+    return torch.cat(out, dim=-1)
+
+
+def _mlp(sd: SD, p: str, x):
+    """text_grounding_net.py:75-81: Linear-SiLU-Linear-SiLU-Linear."""
+    return linear(sd, p + ".4", F.silu(linear(sd, p + ".2", F.silu(linear(sd, p + ".0", x)))))
+
+
+def unifusion(sd: SD, p: str, gi: Dict[str, torch.Tensor], flags: Dict[str, bool]):
+    """UniFusion.forward in eval mode, text_grounding_net.py:185-313, for all-zero `segs` (the
+    ConvNeXt branch then contributes exactly the null feature, :279-283).
+    flags: test_drop_{boxes,points,scribbles,masks} of the config."""
+    boxes, masks, text = gi["boxes"], gi["masks"], gi["positive_embeddings"]
+    scribbles, polygons, segs, points = gi["scribbles"], gi["polygons"], gi["segs"], gi["points"]
+    B, N, _ = boxes.shape
+    m = masks.unsqueeze(-1)
+    drop_box = flags.get("test_drop_boxes", False)
+    drop_point = flags.get("test_drop_points", False)
+    drop_scribble = flags.get("test_drop_scribbles", True)
+    drop_polygons = flags.get("test_drop_masks", False)
+    drop_segs = drop_polygons
+    if drop_point and drop_box and drop_scribble and drop_polygons and drop_segs:
+        drop_box = False
+    if points is None:
+        points = (boxes[:, :, :2] + boxes[:, :, 2:]) / 2.0
+    text = text * m + (1 - m) * sd[p + ".null_positive_feature"].view(1, 1, -1)
+
+    def sub(emb, msk, null):
+        return emb * msk + (1 - msk) * sd[p + "." + null].view(1, 1, -1)
+
+    zeros = torch.zeros_like(m)
+    e_box = sub(fourier_embed(boxes), zeros if drop_box else m, "null_position_feature")
+    e_pt = sub(fourier_embed(points), zeros if drop_point else m, "null_point_feature")
+    m_s = zeros if drop_scribble else ((scribbles.sum(-1, keepdim=True) + m) > 0).float()
+    e_s = sub(fourier_embed(scribbles), m_s, "null_scribble_feature")
+    m_p = zeros if drop_polygons else ((polygons.sum(-1, keepdim=True) + m) > 0).float()
+    e_p = sub(fourier_embed(polygons), m_p, "null_polygon_feature")
+    if not drop_segs and bool((segs.sum(dim=(1, 2, 3)) > 0).any()):
+        raise NotImplementedError("torch_oracle.unifusion: non-zero segs (ConvNeXt branch) not restated")
+    seg = sd[p + ".null_seg_feature"].view(1, 1, -1).repeat(B, 64, 1) + sd[p + ".pos_embedding"]
+    objs = [
+        _mlp(sd, p + ".linears_list.0", torch.cat([text, e_box], -1)),
+        _mlp(sd, p + ".linears_list.1", torch.cat([text, e_pt], -1)),
+        _mlp(sd, p + ".linears_list.2", torch.cat([text, e_s], -1)),
+        _mlp(sd, p + ".linears_list.3", torch.cat([text, e_p], -1)),
+        _mlp(sd, p + ".linears_list.4", seg),
+    ]
+    return torch.cat(objs, dim=1), bool(drop_box and drop_polygons)
+
+
+def null_grounding_input(gi: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """GroundingNetInput.get_null_input, text_grounding_tokinzer_input.py:56-93: zeros of the same shapes."""
+    return {k: torch.zeros_like(v) if k != "segs" else v * 0 for k, v in gi.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# UNetModel.forward_single_input, openaimodel.py:482-563
+# ------------------------------------------------------------------------------------------------
+def _run_block(sd: SD, blk: str, h, emb, ctx, objs, scale):
+    i = 0
+    while True:
+        q = f"{blk}.{i}"
+        if q + ".in_layers.0.weight" in sd:
+            h = resblock(sd, q, h, emb)
+        elif q + ".proj_in.weight" in sd:
+            h = spatial_transformer(sd, q, h, ctx, objs, scale)
+        elif q + ".op.weight" in sd:
+            h = downsample(sd, q, h)
+        elif q + ".conv.weight" in sd:
+            h = upsample(sd, q, h)
+        elif q + ".weight" in sd and i == 0:  # input_blocks.0.0: the first conv
+            h = F.conv2d(h, sd[q + ".weight"], sd[q + ".bias"], padding=1)
+        else:
+            break
+        i += 1
+    return h
+
+
+def unet_forward(sd: SD, x, timesteps, context, gi: Dict[str, torch.Tensor], flags: Dict[str, bool],
+                 scale: float = 1.0, first_conv: Optional[Dict[str, torch.Tensor]] = None):
+    """gi: grounding dict (pass null_grounding_input(...) for the CFG-uncond branch, :483-487).
+    scale: the fusers' `.scale` (set_alpha_scale).  first_conv: SD1.5 weights swapped in on alpha=0
+    steps (restore_first_conv_from_SD, :469-480)."""
+    if first_conv is not None:
+        sd = dict(sd)
+        sd["input_blocks.0.0.weight"] = first_conv["weight"]
+        sd["input_blocks.0.0.bias"] = first_conv["bias"]
+    objs, _ = unifusion(sd, "position_net", gi, flags)
+    emb = linear(sd, "time_embed.2", F.silu(linear(sd, "time_embed.0", timestep_embedding(timesteps, 320))))
+    h = x
+    hs = []
+    i = 0
+    while f"input_blocks.{i}.0.weight" in sd or f"input_blocks.{i}.0.in_layers.0.weight" in sd \
+            or f"input_blocks.{i}.0.op.weight" in sd:
+        h = _run_block(sd, f"input_blocks.{i}", h, emb, context, objs, scale)
+        hs.append(h)
+        i += 1
+    h = _run_block(sd, "middle_block", h, emb, context, objs, scale)
+    i = 0
+    while f"output_blocks.{i}.0.in_layers.0.weight" in sd:
+        skip = hs.pop()
+        b = torch.tanh(sd[f"scaleu_b_{i}"]) + 1
+        s = torch.tanh(sd[f"scaleu_s_{i}"]) + 1
+        h = torch.einsum("bchw,c->bchw", h, b)
+        skip = fourier_filter(skip, 1, s)
+        h = torch.cat([h, skip], dim=1)
+        h = _run_block(sd, f"output_blocks.{i}", h, emb, context, objs, scale)
+        i += 1
+    h = F.silu(F.group_norm(h.float(), 32, sd["out.0.weight"], sd["out.0.bias"], 1e-5))
+    return F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# samplers: ldm/models/diffusion/plms.py, plms_instance.py; utils/model.py:83-117
+# ------------------------------------------------------------------------------------------------
+def alphas_cumprod(linear_start=0.00085, linear_end=0.012, T=1000):
+    """ddpm.py:21-36 + util.py:31-34 (fp64 -> fp32)."""
+    betas = (torch.linspace(linear_start ** 0.5, linear_end ** 0.5, T, dtype=torch.float64) ** 2).numpy()
+    return torch.tensor(np.cumprod(1. - betas, axis=0), dtype=torch.float32)
+
+
+def alpha_schedule(length, alpha_type):
+    n0 = int(alpha_type[0] * length)
+    n1 = int(alpha_type[1] * length)
+    decay = list(np.arange(start=0, stop=1, step=1 / n1)[::-1]) if n1 else []
+    return [1] * n0 + decay + [0] * (length - n0 - n1)
+
+
+def plms_sample(eval_fn: Callable, inputs: List[dict], uc, S: int, guidance: float, mis: float,
+                alpha_type=None):
+    """eval_fn(input_dict, alpha) -> eps.  inputs: [global, inst_1..] (one entry without MIS).
+    Restates plms_instance.py:65-212 (== plms.py:72-167 when mis == 0)."""
+    acp = alphas_cumprod()
+    steps = np.asarray(list(range(0, 1000, 1000 // S))) + 1                  # util.py:55-70
+    a = acp[steps]
+    a_prev = torch.tensor([acp[0].item()] + acp[steps[:-1]].tolist(), dtype=torch.float32)
+    time_range = np.flip(steps)
+    total = len(steps)
+    alphas = alpha_schedule(total, alpha_type) if alpha_type is not None else [1] * total
+    mis_step = int(total * mis)
+
+    def model_out(inp, alpha):
+        e = eval_fn(inp, alpha)
+        if uc is not None and guidance != 1:
+            e_u = eval_fn(dict(x=inp["x"], timesteps=inp["timesteps"], context=uc), alpha)
+            e = e_u + guidance * (e - e_u)
+        return e
+
+    def step(inp, old, i):
+        index = total - i - 1
+        b = inp["x"].shape[0]
+        x = inp["x"].clone()
+        t = torch.full((b,), int(time_range[i]), dtype=torch.long)
+        t_next = torch.full((b,), int(time_range[min(i + 1, total - 1)]), dtype=torch.long)
+        at, ap = a[index], a_prev[index]
+
+        def x_prev_of(e):
+            pred_x0 = (x - torch.sqrt(1. - at) * e) / at.sqrt()
+            return ap.sqrt() * pred_x0 + (1. - ap).sqrt() * e
+
+        inp["timesteps"] = t
+        e_t = model_out(inp, alphas[i])
+        if len(old) == 0:
+            inp["x"] = x_prev_of(e_t)
+            inp["timesteps"] = t_next
+            e_p = (e_t + model_out(inp, alphas[i])) / 2
+        elif len(old) == 1:
+            e_p = (3 * e_t - old[-1]) / 2
+        elif len(old) == 2:
+            e_p = (23 * e_t - 16 * old[-1] + 5 * old[-2]) / 12
+        else:
+            e_p = (55 * e_t - 59 * old[-1] + 37 * old[-2] - 9 * old[-3]) / 24
+        inp["x"] = x_prev_of(e_p)
+        old.append(e_t)
+        if len(old) >= 4:
+            old.pop(0)
+
+    olds = [[] for _ in inputs]
+    for k, inp in enumerate(inputs):
+        for i in range(mis_step):
+            step(inp, olds[k], i)
+    inputs[0]["x"] = torch.mean(torch.stack([inp["x"] for inp in inputs]), dim=0)
+    for i in range(mis_step, total):
+        step(inputs[0], olds[0], i)
+    return inputs[0]["x"]

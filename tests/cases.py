@@ -1,0 +1,97 @@
+"""Seeded parity cases shared by (1) oracle/make_golden.py, which runs them through the reference's
+own modules on the CPU and commits the outputs under tests/golden/, (2) the CPU tests of the
+plain-torch restatement (oracle/torch_oracle.py) and (3) the `-m gpu` tests of the CUDA modules.
+
+A case names a reference class (by its import path inside `ldm/...`), constructor arguments and
+seeded inputs; because the mirror classes keep the reference's signatures, the *same* driver code
+builds and calls either implementation.
+"""
+from __future__ import annotations
+
+import zlib
+from typing import Dict
+
+import torch
+
+WEIGHT_SEED = 1
+
+
+def synth_input(case: str, key: str, shape, scale: float = 1.0) -> torch.Tensor:
+    g = torch.Generator(device="cpu").manual_seed(zlib.crc32(f"{case}/{key}".encode()) & 0x7FFFFFFF)
+    return torch.randn(tuple(shape), generator=g) * scale
+
+
+# name -> spec.  `module` is "<python module under ldm.modules>:<class>".
+MODULE_CASES: Dict[str, dict] = {
+    "gated_sa_L0": dict(module="attention:GatedSelfAttentionDense", args=(320, 768, 8, 40),
+                        kwargs=dict(efficient_attention=True),
+                        inputs=dict(x=(2, 256, 320), objs=(2, 184, 768))),
+    "gated_sa_L2": dict(module="attention:GatedSelfAttentionDense", args=(1280, 768, 8, 160),
+                        kwargs=dict(efficient_attention=True),
+                        inputs=dict(x=(2, 64, 1280), objs=(2, 184, 768))),
+    "self_attn_L1": dict(module="attention:SelfAttention", args=(640,), kwargs=dict(heads=8, dim_head=80, efficient_attention=True),
+                         inputs=dict(x=(2, 256, 640))),
+    "cross_attn_L1": dict(module="attention:CrossAttention", args=(640, 768, 768),
+                          kwargs=dict(heads=8, dim_head=80, efficient_attention=True),
+                          inputs=dict(x=(2, 256, 640), key=(2, 77, 768)), same_kv=True),
+    "ff_L0": dict(module="attention:FeedForward", args=(320,), kwargs=dict(glu=True), inputs=dict(x=(2, 256, 320))),
+    "btb_L1": dict(module="attention:BasicTransformerBlock", args=(640, 768, 768, 8, 80, "gatedSA"),
+                   kwargs=dict(efficient_attention=True),
+                   inputs=dict(x=(2, 256, 640), context=(2, 77, 768), objs=(2, 184, 768))),
+    "st_L0": dict(module="attention:SpatialTransformer", args=(320, 768, 768, 8, 40),
+                  kwargs=dict(depth=1, fuser_type="gatedSA", efficient_attention=True),
+                  inputs=dict(x=(2, 320, 16, 16), context=(2, 77, 768), objs=(2, 184, 768))),
+    "resblock_same": dict(module="diffusionmodules.openaimodel:ResBlock", args=(320, 1280, 0),
+                          kwargs=dict(out_channels=320), inputs=dict(x=(2, 320, 16, 16), emb=(2, 1280))),
+    "resblock_skip": dict(module="diffusionmodules.openaimodel:ResBlock", args=(960, 1280, 0),
+                          kwargs=dict(out_channels=640), inputs=dict(x=(2, 960, 8, 8), emb=(2, 1280))),
+    "upsample": dict(module="diffusionmodules.openaimodel:Upsample", args=(320, True),
+                     kwargs=dict(out_channels=320), inputs=dict(x=(2, 320, 8, 8))),
+    "downsample": dict(module="diffusionmodules.openaimodel:Downsample", args=(320, True),
+                       kwargs=dict(out_channels=320), inputs=dict(x=(2, 320, 16, 16))),
+}
+
+# Fourier_filter(x, threshold=1, scale) cases (openaimodel.py:25-48): shape, scale
+FOURIER_CASES = {
+    "fourier_pow2": dict(shape=(2, 64, 16, 16), scale=1.3),
+    "fourier_npow2": dict(shape=(1, 64, 12, 12), scale=0.6),
+}
+
+# UniFusion cases: flavor (test-time drop flags of configs/test_<flavor>.yaml), batch, instances
+UNIFUSION_CASES = {
+    "unifusion_box": dict(flavor="box", batch=2, n=3, seed=5),
+    "unifusion_point": dict(flavor="point", batch=2, n=3, seed=6),
+    "unifusion_scribble": dict(flavor="scribble", batch=2, n=3, seed=7),
+}
+
+# whole-UNet cases (B=1, 64x64 latent, box flavour, 2 instances)
+UNET_CASE = dict(flavor="box", batch=1, n=2, seed=11, t=601, weight_seed=0)
+
+# sampler cases (config 1 of BASELINE.json and a short plain-PLMS run)
+SAMPLER_CASES = {
+    "plms_S4": dict(S=4, n=1, mis=0.0, batch=1, seed=21, guidance=7.5, alpha_type=[0.8, 0.0, 0.2]),
+    "mis_S10": dict(S=10, n=1, mis=0.36, batch=1, seed=22, guidance=7.5, alpha_type=[0.8, 0.0, 0.2]),
+}
+
+
+def build_inputs(name: str, spec: dict) -> Dict[str, torch.Tensor]:
+    ins = {k: synth_input(name, k, shp) for k, shp in spec["inputs"].items()}
+    if spec.get("same_kv"):
+        ins["value"] = ins["key"]
+    return ins
+
+
+def run_module_case(name: str, spec: dict, cls, device="cpu", dtype=torch.float32, prefix_loader=None):
+    """Build `cls` (reference or mirror), load the case's synthetic weights, call forward."""
+    from instancediffusion_b200.weights import load_synthetic
+    mod = cls(*spec["args"], **spec.get("kwargs", {}))
+    load_synthetic(mod, WEIGHT_SEED, prefix=name + ".")
+    mod = mod.to(device).eval()
+    ins = {k: v.to(device=device, dtype=dtype) for k, v in build_inputs(name, spec).items()}
+    with torch.no_grad():
+        if "key" in ins:
+            kv = ins["key"]
+            out = mod(ins["x"], kv, kv)
+        else:
+            out = mod(**ins)
+    return out
