@@ -92,6 +92,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the plain-torch restatement of the reference path on the host cores
 # ------------------------------------------------------------------------------------------------
+_CPU_STATE: dict = {}
+
+
 def cpu_forward_seconds(n_forwards: int = 2, threads: int | None = None):
     """Times `n_forwards` steady-state UNet forwards (B=1, 512^2, fp32) of oracle/torch_oracle.py --
     the CPU restatement of the reference's forward_single_input -- after one untimed call."""
@@ -101,9 +104,12 @@ def cpu_forward_seconds(n_forwards: int = 2, threads: int | None = None):
     from instancediffusion_b200.ldm.modules.diffusionmodules.openaimodel import UNetModel
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    with torch.device("meta"):
-        m = UNetModel(**unet_config("box"))
-    sd = {k: synth_tensor(k, tuple(v.shape), 0) for k, v in m.state_dict().items() if "convnext" not in k}
+    if "sd" not in _CPU_STATE:
+        with torch.device("meta"):
+            m = UNetModel(**unet_config("box"))
+        _CPU_STATE["sd"] = {k: synth_tensor(k, tuple(v.shape), 0) for k, v in m.state_dict().items()
+                            if "convnext" not in k}
+    sd = _CPU_STATE["sd"]
     gb = synthetic.make_grounding_batch(1, N_INST, 3, "box")
     gi = dict(boxes=gb["boxes"], masks=gb["masks"], positive_embeddings=gb["text_embeddings"],
               scribbles=gb["scribbles"], polygons=gb["polygons"], segs=gb["segs"], points=gb["points"])

@@ -125,8 +125,8 @@ def test_unet_eps_matches_reference_golden(cuda_device, unet):
     # batched cond+uncond == separate forwards (per-sample independence of every op)
     both = unet.forward_batched([dict(x=inp["x"], timesteps=ts, context=inp["context"], grounding_input=gi),
                                  dict(x=inp["x"], timesteps=ts, context=uc)])
-    _report(both[0], eps_c.cpu(), "batched cond == single", 2e-3, 5e-3)
-    _report(both[1], eps_u.cpu(), "batched uncond == single", 2e-3, 5e-3)
+    _report(both[0], eps_c.cpu(), "batched cond == single", 1e-2, 2e-2)
+    _report(both[1], eps_u.cpu(), "batched uncond == single", 1e-2, 2e-2)
     # alpha = 0: fusers off + SD1.5 first conv (openaimodel.py:469-480)
     set_alpha_scale(unet, 0)
     unet.set_sd_first_conv(unet._sd_conv)
