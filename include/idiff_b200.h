@@ -86,9 +86,11 @@ int idiff_attention(const idiff_attn_args* args, void* stream);
  * Normalisation (HBM-bound passes)
  *   idiff_groupnorm: GroupNorm32 (util.py:223-225, eps 1e-5) / Normalize (attention.py:75-76,
  *   eps 1e-6) over NHWC fp16, statistics in fp32, optional fused SiLU (openaimodel.py:184,208).
- *   stats_ws: B*groups*2 floats of scratch (zeroed by the call).
- *   idiff_layernorm: nn.LayerNorm(C) (attention.py:294-295,320-322), one warp per row.
+ *   stats_ws: idiff_groupnorm_ws_floats(batch, groups) floats of scratch (per-chunk partial
+ *   sums, reduced in a fixed order: results are bit-reproducible and batch-invariant).
+ *   idiff_layernorm: nn.LayerNorm(C) (attention.py:294-295,320-322), rows held in registers.
  * ------------------------------------------------------------------------------------------- */
+long idiff_groupnorm_ws_floats(int batch, int groups);
 int idiff_groupnorm(const void* x, void* y, const float* gamma, const float* beta, float* stats_ws,
                     int batch, int hw, int channels, int groups, float eps, int fuse_silu,
                     void* stream);
@@ -100,9 +102,11 @@ int idiff_layernorm(const void* x, void* y, const float* gamma, const float* bet
  *   out[..., :C1]      = h * (tanh(b_c) + 1)
  *   out[..., C1:C1+C2] = Fourier_filter(skip, threshold=1, scale=s) = skip + (s-1) * P_low(skip)
  * with P_low the real part of the inverse DFT restricted to bins {-1,0}x{-1,0} (7 real
- * reductions per (b,c) plane; closed form of openaimodel.py:25-48).  coef_ws: B*C2*8 floats.
+ * reductions per (b,c) plane; closed form of openaimodel.py:25-48).
+ * coef_ws: idiff_scaleu_ws_floats(batch, c2) floats of scratch.
  * b1: per-channel factor tanh(b)+1 (C1 floats, device); s: tanh(scaleu_s)+1 (host scalar).
  * ------------------------------------------------------------------------------------------- */
+long idiff_scaleu_ws_floats(int batch, int c2);
 int idiff_scaleu_concat(const void* h, const void* skip, void* out, const float* b1, float s,
                         float* coef_ws, int batch, int height, int width, int c1, int c2,
                         void* stream);

@@ -51,6 +51,8 @@ SIGNATURES = {
     "idiff_gemm": (_i, [C.POINTER(GemmArgs), _vp]),
     "idiff_attention": (_i, [C.POINTER(AttnArgs), _vp]),
     "idiff_groupnorm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    "idiff_groupnorm_ws_floats": (_l, [_i, _i]),
+    "idiff_scaleu_ws_floats": (_l, [_i, _i]),
     "idiff_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "idiff_scaleu_concat": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp]),
     "idiff_nchw_f32_to_nhwc_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

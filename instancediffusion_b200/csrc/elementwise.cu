@@ -1,4 +1,4 @@
-// HBM-bound helpers of the sampling hot path: ScaleU (closed-form Fourier filter), layout
+// HBM-bound helpers of the sampling hot path (ScaleU lives in scaleu.cu): layout
 // conversion, nearest-2x upsample, stride-2 im2col, UniFusion Fourier embedder, timestep
 // embedding and the fused PLMS sampler update.  Reference citations are at each kernel.
 #include "../../include/idiff_b200.h"
@@ -8,113 +8,6 @@
 namespace idiff {
 
 constexpr float kTwoPi = 6.283185307179586f;
-
-// ---------------------------------------------------------------------------------------------
-// ScaleU (openaimodel.py:519-539) with Fourier_filter (:25-48) in closed form:
-//   filter(x) = x + (s-1) * P_low(x),  P_low = Re IDFT of the bins (fy,fx) in {-1,0}^2
-// Per (b,c) plane seven real sums are needed:
-//   S0=sum x, Ac=sum x cos(tx), As=sum x sin(tx), Bc=sum x cos(py), Bs=sum x sin(py),
-//   Cc=sum x cos(tx+py), Cs=sum x sin(tx+py),   tx=2*pi*x/W, py=2*pi*y/H
-// and P_low(y,x) = (S0 + Ac cos tx + As sin tx + Bc cos py + Bs sin py
-//                   + Cc cos(tx+py) + Cs sin(tx+py)) / (H*W).
-// ---------------------------------------------------------------------------------------------
-constexpr int SU_THREADS = 256;
-
-__global__ void __launch_bounds__(SU_THREADS)
-scaleu_coef_kernel(const __half2* __restrict__ skip, float* __restrict__ coef, int H, int W, int C,
-                   int pix_per_block) {
-  __shared__ float tab[4 * 128];  // cos tx, sin tx, cos py, sin py
-  float* ctx = tab;
-  float* stx = tab + 128;
-  float* cpy = tab + 256;
-  float* spy = tab + 384;
-  for (int i = threadIdx.x; i < W; i += SU_THREADS) sincosf(kTwoPi * i / W, &stx[i], &ctx[i]);
-  for (int i = threadIdx.x; i < H; i += SU_THREADS) sincosf(kTwoPi * i / H, &spy[i], &cpy[i]);
-  __syncthreads();
-  const int b = blockIdx.y;
-  const int hw = H * W;
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(hw, p0 + pix_per_block);
-  const int CP = C >> 1;
-  const __half2* xb = skip + (long)b * hw * CP;
-  for (int cp = threadIdx.x; cp < CP; cp += SU_THREADS) {
-    float a0[7], a1[7];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) a0[k] = a1[k] = 0.f;
-    for (int pix = p0; pix < p1; ++pix) {
-      const int yy = pix / W, xx = pix - yy * W;
-      const float cx = ctx[xx], sx = stx[xx], cy = cpy[yy], sy = spy[yy];
-      const float cxy = cx * cy - sx * sy, sxy = sx * cy + cx * sy;
-      const float2 v = __half22float2(xb[(long)pix * CP + cp]);
-      const float wgt[7] = {1.f, cx, sx, cy, sy, cxy, sxy};
-#pragma unroll
-      for (int k = 0; k < 7; ++k) {
-        a0[k] += v.x * wgt[k];
-        a1[k] += v.y * wgt[k];
-      }
-    }
-    float* dst = coef + ((long)b * C + 2 * cp) * 8;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      atomicAdd(dst + k, a0[k]);
-      atomicAdd(dst + 8 + k, a1[k]);
-    }
-  }
-}
-
-// one thread per 8 output channels; out is (B, HW, C1+C2)
-__global__ void __launch_bounds__(SU_THREADS)
-scaleu_apply_kernel(const uint4* __restrict__ h, const uint4* __restrict__ skip, uint4* __restrict__ out,
-                    const float* __restrict__ b1, const float* __restrict__ coef, float s_minus_1,
-                    int B, int H, int W, int C1, int C2) {
-  const int CV1 = C1 >> 3, CV2 = C2 >> 3, CVO = CV1 + CV2;
-  const long total = (long)B * H * W * CVO;
-  const float inv_hw = 1.0f / (float)(H * W);
-  for (long i = (long)blockIdx.x * SU_THREADS + threadIdx.x; i < total; i += (long)gridDim.x * SU_THREADS) {
-    const int cv = (int)(i % CVO);
-    const long bp = i / CVO;  // b*HW + pix
-    uint32_t o[4];
-    if (cv < CV1) {
-      const uint4 v = h[bp * CV1 + cv];
-      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_half2(u[j]);
-        const int c = cv * 8 + 2 * j;
-        o[j] = pack_half2(f.x * __ldg(b1 + c), f.y * __ldg(b1 + c + 1));
-      }
-    } else {
-      const int cv2 = cv - CV1;
-      const int b = (int)(bp / (H * W));
-      const int pix = (int)(bp - (long)b * H * W);
-      const int yy = pix / W, xx = pix - yy * W;
-      float sx, cx, sy, cy;
-      sincosf(kTwoPi * xx / W, &sx, &cx);
-      sincosf(kTwoPi * yy / H, &sy, &cy);
-      const float cxy = cx * cy - sx * sy, sxy = sx * cy + cx * sy;
-      const uint4 v = skip[bp * CV2 + cv2];
-      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-      float r[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_half2(u[j]);
-        r[2 * j] = f.x;
-        r[2 * j + 1] = f.y;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float* cf = coef + ((long)b * C2 + cv2 * 8 + j) * 8;
-        const float4 c0 = *reinterpret_cast<const float4*>(cf);
-        const float4 c1 = *reinterpret_cast<const float4*>(cf + 4);
-        const float plow = (c0.x + c0.y * cx + c0.z * sx + c0.w * cy + c1.x * sy + c1.y * cxy + c1.z * sxy) * inv_hw;
-        r[j] += s_minus_1 * plow;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = pack_half2(r[2 * j], r[2 * j + 1]);
-    }
-    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // layout conversion
@@ -298,27 +191,6 @@ static inline int grid_for(long total, int threads) {
 }  // namespace idiff
 
 using namespace idiff;
-
-extern "C" int idiff_scaleu_concat(const void* h, const void* skip, void* out, const float* b1, float s,
-                                   float* coef_ws, int batch, int height, int width, int c1, int c2,
-                                   void* stream) {
-  IDIFF_REQUIRE(h && skip && out && b1 && coef_ws, "idiff_scaleu_concat: null pointer argument");
-  IDIFF_REQUIRE(c1 % 8 == 0 && c2 % 8 == 0, "idiff_scaleu_concat: channels must be multiples of 8");
-  IDIFF_REQUIRE(height <= 128 && width <= 128, "idiff_scaleu_concat: H,W <= 128 supported");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  IDIFF_CHECK_CUDA(cudaMemsetAsync(coef_ws, 0, sizeof(float) * 8 * (size_t)batch * c2, st));
-  const int hw = height * width;
-  int ppb = (32768 + c2 - 1) / c2;
-  const int chunks = (hw + ppb - 1) / ppb;
-  scaleu_coef_kernel<<<dim3(chunks, batch), SU_THREADS, 0, st>>>(reinterpret_cast<const __half2*>(skip),
-                                                              coef_ws, height, width, c2, ppb);
-  const long total = (long)batch * hw * ((c1 + c2) / 8);
-  scaleu_apply_kernel<<<grid_for(total, SU_THREADS), SU_THREADS, 0, st>>>(
-      reinterpret_cast<const uint4*>(h), reinterpret_cast<const uint4*>(skip), reinterpret_cast<uint4*>(out),
-      b1, coef_ws, s - 1.0f, batch, height, width, c1, c2);
-  IDIFF_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
 
 extern "C" int idiff_nchw_f32_to_nhwc_f16(const float* x, void* y, int batch, int c, int hw, int c_pad,
                                           void* stream) {

@@ -1,100 +1,239 @@
 // HBM-bound normalisation passes over fp16 token-major (NHWC) activations.
 //   GroupNorm32 / Normalize : util.py:223-225 (eps 1e-5, fp32 statistics), attention.py:75-76 (eps 1e-6)
 //   LayerNorm               : attention.py:294-295, 320-322
-// Statistics are accumulated in fp32.  SiLU (openaimodel.py:184,208,462) is fused into the
-// GroupNorm apply pass.
+// Statistics are accumulated in fp32 in a fixed order (no floating-point atomics), so results
+// are bit-reproducible and independent of how many samples share a launch.  SiLU
+// (openaimodel.py:184,208,462) is fused into the GroupNorm apply pass.
+//
+// Thread mapping (both GroupNorm passes): a CTA has k * CV threads, CV = C/8 16-byte vectors per
+// pixel; thread (r, cv) owns vector cv of pixels r, r+k, ... of the CTA's pixel chunk, so every
+// warp-wide request is a run of consecutive 16-byte vectors and each thread keeps several
+// independent loads in flight.
 #include "../../include/idiff_b200.h"
 #include "common.cuh"
 #include "host.cuh"
 
 namespace idiff {
 
-constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_GROUPS = 32;
+constexpr int GN_MAX_CHUNKS = 64;
 
-// grid (chunks, B). Each thread owns channel pairs cp = t, t+256, ... and walks the pixel chunk.
-__global__ void __launch_bounds__(GN_THREADS)
-gn_stats_kernel(const __half2* __restrict__ x, float* __restrict__ stats, int hw, int C, int groups,
-                int pix_per_block) {
-  __shared__ float sm[GN_MAX_GROUPS * 2];
-  const int b = blockIdx.y;
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(hw, p0 + pix_per_block);
-  const int CP = C >> 1;
-  const int cpg = C / groups;
-  if (threadIdx.x < groups * 2) sm[threadIdx.x] = 0.f;
-  __syncthreads();
-  const __half2* xb = x + (long)b * hw * CP;
-  for (int cp = threadIdx.x; cp < CP; cp += GN_THREADS) {
-    float s = 0.f, ss = 0.f;
-    for (int pix = p0; pix < p1; ++pix) {
-      const float2 v = __half22float2(xb[(long)pix * CP + cp]);
-      s += v.x + v.y;
-      ss += v.x * v.x + v.y * v.y;
-    }
-    const int g = (2 * cp) / cpg;
-    atomicAdd(&sm[2 * g], s);
-    atomicAdd(&sm[2 * g + 1], ss);
+IDIFF_DEVICE void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = unpack_half2(u[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
   }
-  __syncthreads();
-  if (threadIdx.x < groups * 2) atomicAdd(&stats[(long)b * groups * 2 + threadIdx.x], sm[threadIdx.x]);
 }
 
-// grid (chunks, B); dynamic smem: 2*C floats (per-channel scale / shift).
-__global__ void __launch_bounds__(GN_THREADS)
-gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ gamma,
-                const float* __restrict__ beta, const float* __restrict__ stats, int hw, int C,
-                int groups, float eps, int fuse_silu, int pix_per_block) {
-  extern __shared__ float sm_ab[];
-  float* sa = sm_ab;
-  float* sb = sm_ab + C;
-  const int b = blockIdx.y;
-  const int cpg = C / groups;
-  const float inv_n = 1.0f / (float)((long)cpg * hw);
-  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
-    const int g = c / cpg;
-    const float s = stats[((long)b * groups + g) * 2];
-    const float ss = stats[((long)b * groups + g) * 2 + 1];
-    const float mean = s * inv_n;
-    const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    const float a = rstd * gamma[c];
-    sa[c] = a;
-    sb[c] = beta[c] - mean * a;
-  }
-  __syncthreads();
+// grid (chunks, B), block k*CV.  partial: [B][chunks][groups][2] (sum, sumsq)
+__global__ void __launch_bounds__(512)
+gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int hw, int C, int groups,
+                int pix_per_block, int k) {
+  extern __shared__ float red[];  // [k][C][2]
   const int CV = C >> 3;
+  const int r = threadIdx.x / CV;
+  const int cv = threadIdx.x - r * CV;
+  const int b = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(hw, p0 + pix_per_block);
-  const long base = (long)b * hw * CV;
-  const int total = (p1 - p0) * CV;
-  for (int i = threadIdx.x; i < total; i += GN_THREADS) {
-    const int pix = p0 + i / CV;
-    const int cv = i - (i / CV) * CV;
-    const uint4 v = x[base + (long)pix * CV + cv];
-    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+  const uint4* xb = x + (long)b * hw * CV + cv;
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  int pix = p0 + r;
+  for (; pix + 3 * k < p1; pix += 4 * k) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = xb[(long)(pix + u * k) * CV];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        ss[j] += f[j] * f[j];
+      }
+    }
+  }
+  for (; pix < p1; pix += k) {
+    float f[8];
+    unpack8(xb[(long)pix * CV], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += f[j];
+      ss[j] += f[j] * f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[((r * C) + cv * 8 + j) * 2] = s[j];
+    red[((r * C) + cv * 8 + j) * 2 + 1] = ss[j];
+  }
+  __syncthreads();
+  // one warp per group (round robin), fixed summation order
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int cpg = C / groups;
+  for (int g = warp; g < groups; g += nwarps) {
+    float a = 0.f, q = 0.f;
+    for (int i = lane; i < cpg * k; i += 32) {
+      const int rr = i / cpg, c = g * cpg + (i - rr * cpg);
+      a += red[(rr * C + c) * 2];
+      q += red[(rr * C + c) * 2 + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+      float* dst = partial + (((long)b * gridDim.x + blockIdx.x) * groups + g) * 2;
+      dst[0] = a;
+      dst[1] = q;
+    }
+  }
+}
+
+// grid (chunks, B), block k*CV
+__global__ void __launch_bounds__(512)
+gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ gamma,
+                const float* __restrict__ beta, const float* __restrict__ partial, int hw, int C,
+                int groups, float eps, int fuse_silu, int pix_per_block, int k, int stat_chunks) {
+  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  const int CV = C >> 3;
+  const int b = blockIdx.y;
+  const int cpg = C / groups;
+  if (threadIdx.x < groups) {
+    float a = 0.f, q = 0.f;
+    for (int ch = 0; ch < stat_chunks; ++ch) {
+      const float* src = partial + (((long)b * stat_chunks + ch) * groups + threadIdx.x) * 2;
+      a += src[0];
+      q += src[1];
+    }
+    const float inv_n = 1.0f / (float)((long)cpg * hw);
+    const float mean = a * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int r = threadIdx.x / CV;
+  const int cv = threadIdx.x - r * CV;
+  float sa[8], sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    const int g = c / cpg;
+    const float a = s_rstd[g] * gamma[c];
+    sa[j] = a;
+    sb[j] = beta[c] - s_mean[g] * a;
+  }
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(hw, p0 + pix_per_block);
+  const long base = (long)b * hw * CV + cv;
+  auto norm_store = [&](const uint4& v, long idx) {
+    float f[8];
+    unpack8(v, f);
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 f = unpack_half2(u[j]);
-      const int c = cv * 8 + 2 * j;
-      float r0 = f.x * sa[c] + sb[c];
-      float r1 = f.y * sa[c + 1] + sb[c + 1];
+      float r0 = f[2 * j] * sa[2 * j] + sb[2 * j];
+      float r1 = f[2 * j + 1] * sa[2 * j + 1] + sb[2 * j + 1];
       if (fuse_silu) {
         r0 = silu_f(r0);
         r1 = silu_f(r1);
       }
       o[j] = pack_half2(r0, r1);
     }
-    y[base + (long)pix * CV + cv] = make_uint4(o[0], o[1], o[2], o[3]);
+    y[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  int pix = p0 + r;
+  for (; pix + 3 * k < p1; pix += 4 * k) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = x[base + (long)(pix + u * k) * CV];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) norm_store(v[u], base + (long)(pix + u * k) * CV);
+  }
+  for (; pix < p1; pix += k) norm_store(x[base + (long)pix * CV], base + (long)pix * CV);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm.  Fast path: C in {320, 640, 1280} = 40 * LPR: LPR lanes cooperate on a row, five
+// 16-byte vectors per lane held in registers, 32/LPR rows per warp.  Generic path: one warp per row.
+// ---------------------------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256)
+layernorm40_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, int rows, float eps) {
+  constexpr int C = 40 * LPR;
+  constexpr int CV = C / 8;  // 5 * LPR
+  constexpr int RPW = 32 / LPR;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane - sub * LPR;
+  const int row = warp_global * RPW + sub;
+  const bool ok = row < rows;
+  float v[40];
+  if (ok) {
+    uint4 u[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) u[i] = x[(long)row * CV + l + i * LPR];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      float f[8];
+      unpack8(u[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i * 8 + j] = f[j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 40; ++j) v[j] = 0.f;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 40; ++j) s += v[j];
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / C);
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 40; ++j) {
+    const float d = v[j] - mean;
+    ss += d * d;
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss * (1.0f / C) + eps);
+  if (ok) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int c0 = (l + i * LPR) * 8;
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + c0);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + c0 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + c0);
+      const float4 b1 = *reinterpret_cast<const float4*>(beta + c0 + 4);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float r0 = (v[i * 8 + 2 * j] - mean) * rstd * g[2 * j] + bb[2 * j];
+        const float r1 = (v[i * 8 + 2 * j + 1] - mean) * rstd * g[2 * j + 1] + bb[2 * j + 1];
+        o[j] = pack_half2(r0, r1);
+      }
+      y[(long)row * CV + l + i * LPR] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
-// One warp per row; C % 8 == 0, C <= 8 * 32 * LN_MAX_VEC.
-constexpr int LN_MAX_VEC = 5;  // C <= 1280
+constexpr int LN_MAX_VEC = 5;  // generic path: C <= 1280
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, int rows, int C, float eps) {
+layernorm_generic_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, int rows, int C, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -105,14 +244,12 @@ layernorm_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float
   for (int i = 0; i < LN_MAX_VEC; ++i) {
     const int cv = lane + i * 32;
     if (cv < CV) {
-      const uint4 u = x[(long)row * CV + cv];
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      float f[8];
+      unpack8(x[(long)row * CV + cv], f);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_half2(w[j]);
-        v[i * 8 + 2 * j] = f.x;
-        v[i * 8 + 2 * j + 1] = f.y;
-        s += f.x + f.y;
+      for (int j = 0; j < 8; ++j) {
+        v[i * 8 + j] = f[j];
+        s += f[j];
       }
     }
   }
@@ -153,6 +290,24 @@ layernorm_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float
 
 }  // namespace idiff
 
+// geometry shared by the GroupNorm launches and the workspace-size query
+static void gn_geometry(int batch, int hw, int channels, int* k, int* ppb, int* chunks) {
+  const int CV = channels / 8;
+  int kk = 256 / CV;
+  if (kk < 1) kk = 1;
+  if (kk > hw) kk = hw;
+  // aim at >= ~4 CTAs per SM over the whole launch, at most GN_MAX_CHUNKS chunks per sample
+  int want = (148 * 4 + batch - 1) / batch;
+  if (want > idiff::GN_MAX_CHUNKS) want = idiff::GN_MAX_CHUNKS;
+  if (want < 1) want = 1;
+  int p = (hw + want - 1) / want;
+  p = ((p + kk - 1) / kk) * kk;  // multiple of k
+  if (p < kk) p = kk;
+  *k = kk;
+  *ppb = p;
+  *chunks = (hw + p - 1) / p;
+}
+
 extern "C" int idiff_groupnorm(const void* x, void* y, const float* gamma, const float* beta,
                                float* stats_ws, int batch, int hw, int channels, int groups,
                                float eps, int fuse_silu, void* stream) {
@@ -160,22 +315,30 @@ extern "C" int idiff_groupnorm(const void* x, void* y, const float* gamma, const
   IDIFF_REQUIRE(x && y && gamma && beta && stats_ws, "idiff_groupnorm: null pointer argument");
   IDIFF_REQUIRE(groups > 0 && groups <= GN_MAX_GROUPS && channels % groups == 0,
                 "idiff_groupnorm: bad groups=%d for C=%d", groups, channels);
-  IDIFF_REQUIRE(channels % 8 == 0 && (channels / groups) % 2 == 0,
-                "idiff_groupnorm: C=%d must be a multiple of 8 with an even group size", channels);
+  IDIFF_REQUIRE(channels % 8 == 0 && channels <= 4096, "idiff_groupnorm: C=%d must be a multiple of 8, <= 4096", channels);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  IDIFF_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * groups * batch, s));
-  // ~64K elements per block
-  int ppb = (65536 + channels - 1) / channels;
-  if (ppb < 1) ppb = 1;
-  const int chunks = (hw + ppb - 1) / ppb;
+  int k, ppb, chunks;
+  gn_geometry(batch, hw, channels, &k, &ppb, &chunks);
+  const int threads = k * (channels / 8);
+  const size_t smem = (size_t)k * channels * 2 * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  IDIFF_REQUIRE(smem <= 96 * 1024, "idiff_groupnorm: shared memory %zu too large", smem);
   dim3 grid(chunks, batch);
-  gn_stats_kernel<<<grid, GN_THREADS, 0, s>>>(reinterpret_cast<const __half2*>(x), stats_ws, hw,
-                                              channels, groups, ppb);
-  gn_apply_kernel<<<grid, GN_THREADS, 2 * channels * sizeof(float), s>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), gamma, beta, stats_ws, hw,
-      channels, groups, eps, fuse_silu, ppb);
+  gn_stats_kernel<<<grid, threads, smem, s>>>(reinterpret_cast<const uint4*>(x), stats_ws, hw, channels,
+                                              groups, ppb, k);
+  gn_apply_kernel<<<grid, threads, 0, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y),
+                                           gamma, beta, stats_ws, hw, channels, groups, eps, fuse_silu, ppb,
+                                           k, chunks);
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" long idiff_groupnorm_ws_floats(int batch, int groups) {
+  return (long)batch * idiff::GN_MAX_CHUNKS * groups * 2;
 }
 
 extern "C" int idiff_layernorm(const void* x, void* y, const float* gamma, const float* beta,
@@ -185,9 +348,22 @@ extern "C" int idiff_layernorm(const void* x, void* y, const float* gamma, const
   IDIFF_REQUIRE(channels % 8 == 0 && channels <= 8 * 32 * LN_MAX_VEC,
                 "idiff_layernorm: unsupported C=%d", channels);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int rows_per_block = 8;
-  layernorm_kernel<<<(rows + rows_per_block - 1) / rows_per_block, 256, 0, s>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), gamma, beta, rows, channels, eps);
+  const uint4* xi = reinterpret_cast<const uint4*>(x);
+  uint4* yo = reinterpret_cast<uint4*>(y);
+  const int warps_per_block = 8;
+  auto blocks = [&](int rows_per_warp) {
+    const int rpb = warps_per_block * rows_per_warp;
+    return (rows + rpb - 1) / rpb;
+  };
+  if (channels == 320) {
+    layernorm40_kernel<8><<<blocks(4), 256, 0, s>>>(xi, yo, gamma, beta, rows, eps);
+  } else if (channels == 640) {
+    layernorm40_kernel<16><<<blocks(2), 256, 0, s>>>(xi, yo, gamma, beta, rows, eps);
+  } else if (channels == 1280) {
+    layernorm40_kernel<32><<<blocks(1), 256, 0, s>>>(xi, yo, gamma, beta, rows, eps);
+  } else {
+    layernorm_generic_kernel<<<blocks(1), 256, 0, s>>>(xi, yo, gamma, beta, rows, channels, eps);
+  }
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -161,7 +161,7 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, batch
     if out is None:
         out = torch.empty_like(x)
     if stats_ws is None:
-        stats_ws = torch.empty(batch * groups * 2, dtype=torch.float32, device=x.device)
+        stats_ws = torch.empty(lib.idiff_groupnorm_ws_floats(batch, groups), dtype=torch.float32, device=x.device)
     check(_launch("groupnorm", 0.0, 4.0 * x.numel(), lambda: lib.idiff_groupnorm(
         x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats_ws.data_ptr(), batch, hw, Cc,
         groups, eps, int(silu), _stream())), "idiff_groupnorm")
@@ -193,7 +193,7 @@ def scaleu_concat(h: torch.Tensor, skip: torch.Tensor, b1: torch.Tensor, s: floa
     if out is None:
         out = torch.empty((batch * height * width, c1 + c2), dtype=HALF, device=h.device)
     if coef_ws is None:
-        coef_ws = torch.empty(batch * c2 * 8, dtype=torch.float32, device=h.device)
+        coef_ws = torch.empty(lib.idiff_scaleu_ws_floats(batch, c2), dtype=torch.float32, device=h.device)
     check(_launch("scaleu_concat", 0.0, 4.0 * (h.numel() + skip.numel()), lambda: lib.idiff_scaleu_concat(
         h.data_ptr(), skip.data_ptr(), out.data_ptr(), b1.data_ptr(), float(s), coef_ws.data_ptr(), batch, height,
         width, c1, c2, _stream())), "idiff_scaleu_concat")
