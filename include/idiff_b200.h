@@ -60,6 +60,13 @@ typedef struct {
   int conv_b, conv_h, conv_w, conv_cin;
 } idiff_gemm_args;
 int idiff_gemm(const idiff_gemm_args* args, void* stream);
+/* Optional stream-K scratch (fp32 partial tiles + flags) for load-balancing GEMMs whose tile count
+ * is not a multiple of the SM count.  Caller-owned device memory of at least
+ * idiff_gemm_workspace_bytes(); zeroed by the call (synchronous).  Without it every GEMM runs
+ * data-parallel.  One workspace per process / stream: concurrent GEMMs on different streams must
+ * not share it. */
+long idiff_gemm_workspace_bytes(void);
+int idiff_set_gemm_workspace(void* ptr, long bytes);
 
 /* ---------------------------------------------------------------------------------------------
  * idiff_attention: softmax(Q K^T * scale) V per (batch, head), flash-style online softmax with

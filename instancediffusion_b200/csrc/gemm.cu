@@ -16,7 +16,13 @@
 #include "common.cuh"
 #include "host.cuh"
 
+#include <stdlib.h>
+
 namespace idiff {
+
+namespace v2 {
+int gemm_v2(const idiff_gemm_args* a, cudaStream_t stream);  // gemm2.cu
+}
 
 constexpr int BM = 128;
 constexpr int BK = 64;                    // 64 fp16 = 128 B = one swizzle row
@@ -358,5 +364,12 @@ extern "C" int idiff_gemm(const idiff_gemm_args* a, void* stream) {
   } else {
     IDIFF_REQUIRE(!a->residual, "idiff_gemm: NCHW fp32 output excludes residual");
   }
-  return launch_gemm<128>(a, reinterpret_cast<cudaStream_t>(stream));
+  // gemm2.cu (persistent / stream-K / wide tiles) is the production kernel; the first-generation
+  // kernel in this file stays selectable for A/B measurements (IDIFF_GEMM_V1=1).
+  static const bool use_v1 = []() {
+    const char* e = getenv("IDIFF_GEMM_V1");
+    return e && e[0] == '1';
+  }();
+  if (use_v1) return launch_gemm<128>(a, reinterpret_cast<cudaStream_t>(stream));
+  return v2::gemm_v2(a, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,602 @@
+// GEMM v2 for sm_100a: persistent, stream-K balanced tcgen05 GEMM / implicit-GEMM conv3x3.
+//
+//   out[M, N] = epilogue( A[M, K] . W[N, K]^T )        fp16 operands, fp32 accumulation in TMEM
+//
+// Differences to the first kernel (gemm.cu), driven by the measured shape mix of the UNet
+// (profiles/r1_v0_launches_forward_b8.csv):
+//   * one persistent CTA per SM; work = (128 x BN tile, k-block range) segments.  Full waves of
+//     tiles are processed data-parallel; the ragged last 1-2 waves are split evenly over all CTAs
+//     in units of 64-wide k-blocks ("stream-K"), so 40-, 160- and 320-tile problems no longer leave
+//     most SMs idle.  A tile shared by several CTAs is finished by the CTA that holds its first
+//     k-blocks; the others publish fp32 partials (coalesced, L2-resident) and a per-warp flag, and
+//     the owner adds them in a fixed order -> bit-reproducible.
+//   * BN in {128, 160, 192, 256} chosen per N (320 = 2 x 160, 960 = 5 x 192, 1280 = 5 x 256 ...):
+//     no padded columns, half the A-tile traffic of 128-wide tiles.
+//   * two TMEM accumulator buffers: the epilogue of segment i overlaps the MMAs of segment i+1;
+//     8 epilogue warps (2 per TMEM lane quarter) so short-K layers are not epilogue-bound.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + UMMA issuer,
+// warps 2..9 epilogue.  conv3x3 gathers the A tile tap by tap with a 4-D TMA box (zero fill at
+// the borders), exactly as in gemm.cu.
+#include "../../include/idiff_b200.h"
+#include "common.cuh"
+#include "host.cuh"
+
+namespace idiff {
+namespace v2 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int THREADS = 320;
+constexpr int EPI_WARPS = 8;
+constexpr int CHUNK = 16;  // accumulator columns per tcgen05.ld
+
+struct Params {
+  int M, N, K, KB;
+  int n_tiles, T, T_dp, G;
+  long U_sk;  // stream-K units (k-blocks) = (T - T_dp) * KB
+  // conv geometry
+  int conv, H, W, Bn, PW, PH, PB, tiles_w, tiles_h, kb_per_tap;
+  // epilogue
+  const float* bias;
+  const __half* rowadd;
+  const __half* residual;
+  void* out;
+  int ldo, ldr, ldra, rows_per_batch, flags;
+  float gate;
+  // stream-K fixup
+  float* ws;    // [G][BN/CHUNK][128][CHUNK] fp32 partial tiles
+  int* sflags;  // [G][EPI_WARPS] publish flags (fixed location, self-resetting)
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN <= 128) ? 6 : ((BN <= 192) ? 5 : 4);
+  static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+struct Seg {
+  int tile, kb0, kb1;
+};
+
+// Work iterator shared by the three roles: stream-K range first, then data-parallel tiles.
+struct WorkIter {
+  const Params& p;
+  int cta;
+  long u, u1;  // stream-K cursor / end (units)
+  int dp_next;
+  __device__ WorkIter(const Params& p_, int cta_) : p(p_), cta(cta_) {
+    u = (p.U_sk * cta) / p.G;
+    u1 = (p.U_sk * (cta + 1)) / p.G;
+    dp_next = cta;
+  }
+  __device__ bool next(Seg& s) {
+    if (u < u1) {
+      const int t_local = (int)(u / p.KB);
+      const int kb0 = (int)(u - (long)t_local * p.KB);
+      const long rem = u1 - u;
+      const int kb1 = (rem < (long)(p.KB - kb0)) ? (int)(kb0 + rem) : p.KB;
+      s.tile = p.T_dp + t_local;
+      s.kb0 = kb0;
+      s.kb1 = kb1;
+      u += kb1 - kb0;
+      return true;
+    }
+    if (dp_next < p.T_dp) {
+      s.tile = dp_next;
+      s.kb0 = 0;
+      s.kb1 = p.KB;
+      dp_next += p.G;
+      return true;
+    }
+    return false;
+  }
+};
+
+IDIFF_DEVICE void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+IDIFF_DEVICE int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+IDIFF_DEVICE void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const Params p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta = blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], EPI_WARPS * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_origin = [&](int tile, int& n0, int& m0, int& b0, int& h0, int& w0) {
+    const int n_tile = tile % p.n_tiles;
+    const int m_tile = tile / p.n_tiles;
+    n0 = n_tile * BN;
+    m0 = m_tile * BM;
+    b0 = h0 = w0 = 0;
+    if (p.conv) {
+      const int tw = m_tile % p.tiles_w;
+      const int th = (m_tile / p.tiles_w) % p.tiles_h;
+      const int tb = m_tile / (p.tiles_w * p.tiles_h);
+      b0 = tb * p.PB;
+      h0 = th * p.PH;
+      w0 = tw * p.PW;
+    }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      WorkIter it(p, cta);
+      Seg sg;
+      uint32_t kc = 0;  // running k-block counter over all segments (ring position)
+      while (it.next(sg)) {
+        int n0, m0, b0, h0, w0;
+        tile_origin(sg.tile, n0, m0, b0, h0, w0);
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++kc) {
+          const int s = kc % STAGES;
+          const uint32_t ph = (kc / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          if (p.conv) {
+            const int tap = kb / p.kb_per_tap;
+            const int cb = kb - tap * p.kb_per_tap;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            tma_load_4d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], cb * BK, w0 + kx - 1,
+                        h0 + ky - 1, b0);
+          } else {
+            tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BK, m0);
+          }
+          tma_load_2d(sB + s * C::B_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== UMMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0, 0);
+      WorkIter it(p, cta);
+      Seg sg;
+      uint32_t kc = 0, sc = 0;
+      while (it.next(sg)) {
+        const int acc = sc & 1;
+        mbar_wait(&tmem_empty[acc], ((sc >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++kc) {
+          const int s = kc % STAGES;
+          mbar_wait(&full_bar[s], (kc / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * A_STAGE_BYTES);
+          const uint32_t b_base = smem_u32(sB + s * C::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(a_base + k * 32, 16, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(b_base + k * 32, 16, 1024);
+            umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > sg.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+        ++sc;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2;       // 0..7
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = ew >> 2;      // which half of the tile's columns
+    const int r = quarter * 32 + lane;
+    const bool geglu = (p.flags & IDIFF_EPI_GEGLU) != 0;
+    const bool do_silu = (p.flags & IDIFF_EPI_SILU) != 0;
+    const bool nchw = (p.flags & IDIFF_OUT_F32_NCHW) != 0;
+    const int n_out_total = geglu ? p.N / 2 : p.N;
+    constexpr int NCH = BN / 2 / CHUNK;  // accumulator chunks owned by this warp
+    // Accumulator column of chunk `ch` of this warp.  Plain: a contiguous half of the tile.
+    // GEGLU: value columns [half*BN/4, +BN/4) followed by their gate columns (BN/2 further on), so
+    // that a warp publishes exactly the columns its owner counterpart consumes.
+    auto chunk_col = [&](int ch) -> int {
+      if (!geglu) return half * (BN / 2) + ch * CHUNK;
+      return (ch < NCH / 2) ? (half * (BN / 4) + ch * CHUNK) : (BN / 2 + half * (BN / 4) + (ch - NCH / 2) * CHUNK);
+    };
+
+    WorkIter it(p, cta);
+    Seg sg;
+    uint32_t sc = 0;
+    while (it.next(sg)) {
+      const int acc = sc & 1;
+      int n0, m0, b0, h0, w0;
+      tile_origin(sg.tile, n0, m0, b0, h0, w0);
+      const bool owner = sg.kb0 == 0;
+      const bool complete = owner && sg.kb1 == p.KB;
+      // followers of an incomplete owner segment: the CTAs covering the tile's remaining k-blocks
+      int f0 = 0, f1 = -1;
+      if (owner && !complete) {
+        const long tile_u0 = (long)(sg.tile - p.T_dp) * p.KB;
+        f0 = (int)(((tile_u0 + sg.kb1 + 1) * p.G + p.U_sk - 1) / p.U_sk) - 1;
+        f1 = (int)(((tile_u0 + p.KB) * p.G + p.U_sk - 1) / p.U_sk) - 1;
+      }
+      long out_row = 0;
+      bool row_ok = false;
+      int batch_idx = 0, pix = 0;
+      if (owner) {
+        if (p.conv) {
+          const int pw = r % p.PW;
+          const int ph_ = (r / p.PW) % p.PH;
+          const int pb = r / (p.PW * p.PH);
+          const int b = b0 + pb, h = h0 + ph_, w = w0 + pw;
+          row_ok = (b < p.Bn) && (h < p.H) && (w < p.W);
+          pix = h * p.W + w;
+          out_row = (long)b * p.H * p.W + pix;
+          batch_idx = b;
+        } else {
+          out_row = (long)m0 + r;
+          row_ok = out_row < p.M;
+          batch_idx = (int)(out_row / p.rows_per_batch);
+          pix = (int)(out_row - (long)batch_idx * p.rows_per_batch);
+        }
+      }
+      mbar_wait(&tmem_full[acc], (sc >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + acc * C::ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
+
+      if (!owner) {
+        // ---- publish the fp32 partial of this warp's region: ws[cta][chunk][row][CHUNK] ----
+        float* wsb = p.ws + (long)cta * (BN / CHUNK) * 128 * CHUNK;
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int c0 = chunk_col(ch);
+          uint32_t v[CHUNK];
+          tmem_ld_32x32b_x16(trow + c0, v);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(wsb + ((long)(c0 / CHUNK) * 128 + r) * CHUNK);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            __stcg(dst + q, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                        __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])));
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_gpu(p.sflags + cta * EPI_WARPS + ew, 1);
+      } else {
+        // ---- owner: (optional fixup) + fused epilogue ----
+        if (!complete) {
+          for (int f = f0; f <= f1; ++f) {
+            const int* fl = p.sflags + f * EPI_WARPS + ew;
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(fl) == 0) {
+              if (clock64() - t0 > 8000000000LL) {
+                if (lane == 0) printf("idiff: stream-K fixup timeout cta=%d waits %d\n", cta, f);
+                __trap();
+              }
+            }
+          }
+        }
+        const int nch = geglu ? NCH / 2 : NCH;  // GEGLU: the second half of the chunks are the gates
+#pragma unroll 1
+        for (int ch = 0; ch < nch; ++ch) {
+          const int c0 = chunk_col(ch);  // accumulator column (value column in GEGLU mode)
+          const int out_c = (geglu ? (sg.tile % p.n_tiles) * (BN / 2) : n0) + c0;  // output column
+          if (out_c >= n_out_total) break;  // warp-uniform
+          uint32_t v[CHUNK];
+          uint32_t g[CHUNK];
+          float x[CHUNK];
+          float gx[CHUNK];
+          tmem_ld_32x32b_x16(trow + c0, v);
+          if (geglu) tmem_ld_32x32b_x16(trow + BN / 2 + c0, g);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j) {
+            x[j] = __uint_as_float(v[j]);
+            gx[j] = geglu ? __uint_as_float(g[j]) : 0.f;
+          }
+          if (!complete) {
+            for (int f = f0; f <= f1; ++f) {
+              const float* wsf = p.ws + (long)f * (BN / CHUNK) * 128 * CHUNK;
+              const float4* src = reinterpret_cast<const float4*>(wsf + ((long)(c0 / CHUNK) * 128 + r) * CHUNK);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 t = __ldcg(src + q);
+                x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+              }
+              if (geglu) {
+                const float4* srcg = reinterpret_cast<const float4*>(
+                    wsf + ((long)((BN / 2 + c0) / CHUNK) * 128 + r) * CHUNK);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 t = __ldcg(srcg + q);
+                  gx[4 * q] += t.x; gx[4 * q + 1] += t.y; gx[4 * q + 2] += t.z; gx[4 * q + 3] += t.w;
+                }
+              }
+            }
+          }
+          if (geglu) {
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) {
+              float val = x[j], gat = gx[j];
+              if (p.bias) {
+                val += __ldg(p.bias + n0 + c0 + j);
+                gat += __ldg(p.bias + n0 + BN / 2 + c0 + j);
+              }
+              x[j] = val * gelu_erf_f(gat);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) {
+              const int col = n0 + c0 + j;
+              float val = x[j];
+              if (col < p.N) {
+                if (p.bias) val += __ldg(p.bias + col);
+                if (p.rowadd && row_ok) val += __half2float(p.rowadd[(long)batch_idx * p.ldra + col]);
+              }
+              if (do_silu) val = silu_f(val);
+              x[j] = val;
+            }
+          }
+          if (row_ok) {
+            if (nchw) {
+              float* o = reinterpret_cast<float*>(p.out);
+              const long hw = p.conv ? (long)p.H * p.W : (long)p.rows_per_batch;
+#pragma unroll
+              for (int j = 0; j < CHUNK; ++j) {
+                const int col = out_c + j;
+                if (col < n_out_total) o[((long)batch_idx * n_out_total + col) * hw + pix] = x[j];
+              }
+            } else {
+              __half* o = reinterpret_cast<__half*>(p.out) + out_row * p.ldo + out_c;
+              const __half* res = p.residual ? p.residual + out_row * p.ldr + out_c : nullptr;
+#pragma unroll
+              for (int j8 = 0; j8 < CHUNK / 8; ++j8) {
+                if (out_c + j8 * 8 < n_out_total) {
+                  float y[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) y[j] = x[j8 * 8 + j];
+                  if (res) {
+                    const uint4 rv = *reinterpret_cast<const uint4*>(res + j8 * 8);
+                    const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 f = unpack_half2(ru[j]);
+                      y[2 * j] = f.x + p.gate * y[2 * j];
+                      y[2 * j + 1] = f.y + p.gate * y[2 * j + 1];
+                    }
+                  }
+                  uint4 ov;
+                  ov.x = pack_half2(y[0], y[1]);
+                  ov.y = pack_half2(y[2], y[3]);
+                  ov.z = pack_half2(y[4], y[5]);
+                  ov.w = pack_half2(y[6], y[7]);
+                  *reinterpret_cast<uint4*>(o + j8 * 8) = ov;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+        if (!complete) {
+          // consume the followers' flags so the next launch (or graph replay) starts clean
+          __syncwarp();
+          if (lane == 0)
+            for (int f = f0; f <= f1; ++f) st_release_gpu(p.sflags + f * EPI_WARPS + ew, 0);
+        }
+      }
+      ++sc;
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static void* g_ws = nullptr;
+static long g_ws_bytes = 0;
+static int g_num_sms = 0;
+constexpr long kFlagBytes = 64 * 1024;
+
+static void choose_patch(int H, int W, int* PW, int* PH, int* PB) {
+  int pw = 1;
+  while (pw * 2 <= 128 && (W % (pw * 2)) == 0) pw *= 2;
+  int ph = 1;
+  while (pw * ph * 2 <= 128 && ph < H) ph *= 2;
+  *PW = pw;
+  *PH = ph;
+  *PB = 128 / (pw * ph);
+}
+
+static int pick_bn(int N, bool geglu) {
+  if (geglu || N <= 128) return 128;
+  const int cands[4] = {256, 192, 160, 128};
+  int best = 128;
+  long best_pad = -1;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    const long pad = (long)((N + bn - 1) / bn) * bn;
+    if (best_pad < 0 || pad < best_pad) {
+      best_pad = pad;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+template <int BN>
+static int launch(const idiff_gemm_args* a, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M;
+  p.N = a->N;
+  p.K = a->K;
+  p.KB = (a->K + BK - 1) / BK;
+  p.bias = a->bias;
+  p.rowadd = reinterpret_cast<const __half*>(a->rowadd);
+  p.residual = reinterpret_cast<const __half*>(a->residual);
+  p.out = a->out;
+  p.ldo = a->ldo;
+  p.ldr = a->ldr;
+  p.ldra = a->ldra > 0 ? a->ldra : a->N;
+  p.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : a->M;
+  p.flags = a->flags;
+  p.gate = a->gate;
+
+  CUtensorMap tmA, tmB;
+  int m_tiles;
+  if (a->conv_h > 0) {
+    const int H = a->conv_h, W = a->conv_w, B = a->conv_b, Cn = a->conv_cin;
+    IDIFF_REQUIRE(Cn % BK == 0, "conv3x3: Cin=%d must be a multiple of %d", Cn, BK);
+    IDIFF_REQUIRE(a->K == 9 * Cn, "conv3x3: K=%d must equal 9*Cin=%d", a->K, 9 * Cn);
+    IDIFF_REQUIRE(a->M == B * H * W, "conv3x3: M=%d must equal B*H*W=%d", a->M, B * H * W);
+    p.conv = 1;
+    p.H = H;
+    p.W = W;
+    p.Bn = B;
+    choose_patch(H, W, &p.PW, &p.PH, &p.PB);
+    p.tiles_w = W / p.PW;
+    p.tiles_h = (H + p.PH - 1) / p.PH;
+    const int tiles_b = (B + p.PB - 1) / p.PB;
+    p.kb_per_tap = Cn / BK;
+    p.rows_per_batch = H * W;
+    m_tiles = p.tiles_w * p.tiles_h * tiles_b;
+    const uint64_t dims[4] = {(uint64_t)Cn, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)Cn * 2, (uint64_t)W * Cn * 2, (uint64_t)H * W * Cn * 2};
+    const uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.PW, (uint32_t)p.PH, (uint32_t)p.PB};
+    if (encode_tmap_f16(&tmA, a->a, 4, dims, strides, box)) return -1;
+  } else {
+    m_tiles = (a->M + BM - 1) / BM;
+    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
+    const uint64_t strides[1] = {(uint64_t)a->lda * 2};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
+    if (encode_tmap_f16(&tmA, a->a, 2, dims, strides, box)) return -1;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    const uint64_t strides[1] = {(uint64_t)a->ldw * 2};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    if (encode_tmap_f16(&tmB, a->w, 2, dims, strides, box)) return -1;
+  }
+  p.n_tiles = (a->N + BN - 1) / BN;
+  p.T = p.n_tiles * m_tiles;
+
+  if (g_num_sms == 0) {
+    int dev = 0;
+    IDIFF_CHECK_CUDA(cudaGetDevice(&dev));
+    IDIFF_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // Stream-K needs the fixup workspace (flags in its first 64 KiB, partial tiles after); short-K
+  // problems (fixup cost ~ mainloop) and exact multiples of the SM count stay data-parallel.
+  const long ws_need = kFlagBytes + (long)g_num_sms * 128 * BN * sizeof(float);
+  const bool use_sk = g_ws && g_ws_bytes >= ws_need && p.KB >= 8 && (p.T % g_num_sms) != 0 &&
+                      (long)p.T * p.KB >= g_num_sms;
+  if (use_sk) {
+    p.G = g_num_sms;
+    const int waves = p.T / p.G;
+    p.T_dp = (waves >= 2) ? (waves - 1) * p.G : 0;
+    p.U_sk = (long)(p.T - p.T_dp) * p.KB;
+    p.sflags = reinterpret_cast<int*>(g_ws);
+    p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_ws) + kFlagBytes);
+  } else {
+    p.G = g_num_sms < p.T ? g_num_sms : p.T;
+    p.T_dp = p.T;
+    p.U_sk = 0;
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          C::SMEM_BYTES));
+    attr_set = true;
+  }
+  gemm2_kernel<BN><<<p.G, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gemm_v2(const idiff_gemm_args* a, cudaStream_t stream) {
+  const bool geglu = (a->flags & IDIFF_EPI_GEGLU) != 0;
+  switch (pick_bn(a->N, geglu)) {
+    case 256: return launch<256>(a, stream);
+    case 192: return launch<192>(a, stream);
+    case 160: return launch<160>(a, stream);
+    default: return launch<128>(a, stream);
+  }
+}
+
+}  // namespace v2
+}  // namespace idiff
+
+extern "C" int idiff_set_gemm_workspace(void* ptr, long bytes) {
+  using namespace idiff;
+  if (ptr) {
+    IDIFF_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 255) == 0, "idiff_set_gemm_workspace: pointer must be 256B aligned");
+    // flags live inside the workspace and must start at zero
+    IDIFF_CHECK_CUDA(cudaMemset(ptr, 0, (size_t)bytes));
+  }
+  v2::g_ws = ptr;
+  v2::g_ws_bytes = ptr ? bytes : 0;
+  return 0;
+}
+
+extern "C" long idiff_gemm_workspace_bytes(void) {
+  // 148 SMs x 128 x 256 fp32 partial tiles + flags, rounded up
+  return 256L * 128 * 256 * 4 + (1 << 20);
+}

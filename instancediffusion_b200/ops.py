@@ -35,6 +35,23 @@ def _launch(kind: str, flops: float, nbytes: float, fn):
     return rc
 
 
+_GEMM_WS = {}
+
+
+def _ensure_gemm_workspace(device: torch.device) -> None:
+    """Register the stream-K scratch buffer with the library once per process (allocated outside any
+    CUDA-graph capture: the first GEMM of a process is never issued under capture)."""
+    if _GEMM_WS:
+        return
+    if torch.cuda.is_current_stream_capturing():
+        return
+    lib = _lib.load()
+    n = int(lib.idiff_gemm_workspace_bytes())
+    buf = torch.empty(n, dtype=torch.uint8, device=device)
+    check(lib.idiff_set_gemm_workspace(buf.data_ptr(), n), "idiff_set_gemm_workspace")
+    _GEMM_WS["buf"] = buf
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -63,6 +80,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     lib = _lib.load()
     _req(a, HALF, "a")
     _req(w, HALF, "w")
+    _ensure_gemm_workspace(a.device)
     N, K = w.shape
     if conv is not None:
         B, H, Wd, Cin = conv

@@ -51,6 +51,39 @@ def test_gemm_linear(cuda_device, M, N, K):
     _check(out, ref, 2e-3, 2e-3, f"gemm {M}x{N}x{K}")
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 1280, 11520), (2048, 1280, 5120), (8192, 640, 2560), (2048, 3840, 1280),
+                                   (512, 320, 23040), (19000, 960, 640)])
+def test_gemm_stream_k_shapes(cuda_device, M, N, K):
+    """Tile counts that are not multiples of the SM count: the ragged waves are split over all SMs in
+    k-block units and fixed up through the fp32 workspace; the result must be bit-reproducible."""
+    ops = _ops()
+    a = _randn((M, K), cuda_device, 1.0, 1).half()
+    w = _randn((N, K), cuda_device, 1.0 / math.sqrt(K), 2).half()
+    bias = _randn((N,), cuda_device, 0.5, 3)
+    res = _randn((M, N), cuda_device, 1.0, 4).half()
+    out = ops.gemm(a, w, bias, residual=res, gate=0.5)
+    ref = res.float() + 0.5 * (a.float() @ w.float().t() + bias)
+    _check(out, ref, 2e-3, 2e-3, f"gemm stream-K {M}x{N}x{K}")
+    for _ in range(3):
+        again = ops.gemm(a, w, bias, residual=res, gate=0.5)
+        assert torch.equal(out, again), "stream-K result is not bit-reproducible"
+
+
+def test_gemm_geglu_stream_k(cuda_device):
+    from instancediffusion_b200.packing import pack_geglu
+    ops = _ops()
+    M, C = 2048, 1280
+    a = _randn((M, C), cuda_device, 1.0, 1).half()
+    w = _randn((8 * C, C), cuda_device, 1.0 / math.sqrt(C), 2).half()
+    bias = _randn((8 * C,), cuda_device, 0.5, 3)
+    wp, bp = pack_geglu(w, bias)
+    out = ops.gemm(a, wp, bp, geglu=True)
+    h = a.float() @ w.float().t() + bias
+    x, gate = h.chunk(2, dim=-1)
+    _check(out, x * F.gelu(gate), 3e-3, 3e-3, "geglu stream-K 2048x1280")
+    assert torch.equal(out, ops.gemm(a, wp, bp, geglu=True))
+
+
 def test_gemm_residual_gate_silu(cuda_device):
     ops = _ops()
     M, N, K = 512, 320, 640

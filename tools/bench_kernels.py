@@ -30,6 +30,8 @@ def timed(fn, iters=5):
     ts = []
     for _ in range(iters):
         flush.zero_()
+        # keep the GPU busy (~150 us) while the CPU enqueues, so the events bracket pure device time
+        torch.cuda._sleep(300000)
         s = torch.cuda.Event(enable_timing=True)
         e = torch.cuda.Event(enable_timing=True)
         s.record()
