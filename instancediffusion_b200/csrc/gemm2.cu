@@ -325,65 +325,112 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
         }
+        // Lean epilogue: all per-tile pointers are formed once, bias / row-add / residual arrive as
+        // 16-byte vector loads per 16-column chunk, and mode switches are warp-uniform branches
+        // outside the per-element loops (the first version spent ~40 instructions per element on
+        // address arithmetic and predicates and was issue-bound; see profiles/).
         const int nch = geglu ? NCH / 2 : NCH;  // GEGLU: the second half of the chunks are the gates
+        const int out_col_base = geglu ? (sg.tile % p.n_tiles) * (BN / 2) : n0;
+        __half* o_row = reinterpret_cast<__half*>(p.out) + out_row * p.ldo + out_col_base;
+        const __half* res_row = p.residual ? p.residual + out_row * p.ldr + out_col_base : nullptr;
+        const __half* radd_row = p.rowadd ? p.rowadd + (long)batch_idx * p.ldra + n0 : nullptr;
+        const float* bias_t = p.bias ? p.bias + n0 : nullptr;
+        const float gate = p.gate;
 #pragma unroll 1
         for (int ch = 0; ch < nch; ++ch) {
           const int c0 = chunk_col(ch);  // accumulator column (value column in GEGLU mode)
-          const int out_c = (geglu ? (sg.tile % p.n_tiles) * (BN / 2) : n0) + c0;  // output column
+          const int out_c = out_col_base + c0;
           if (out_c >= n_out_total) break;  // warp-uniform
+          const bool hi_ok = out_c + 8 < n_out_total;  // second 8-column group inside N (N % 8 == 0)
           uint32_t v[CHUNK];
-          uint32_t g[CHUNK];
           float x[CHUNK];
-          float gx[CHUNK];
           tmem_ld_32x32b_x16(trow + c0, v);
-          if (geglu) tmem_ld_32x32b_x16(trow + BN / 2 + c0, g);
-          tmem_ld_wait();
+          if (geglu) {
+            uint32_t g[CHUNK];
+            float gx[CHUNK];
+            tmem_ld_32x32b_x16(trow + BN / 2 + c0, g);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < CHUNK; ++j) {
-            x[j] = __uint_as_float(v[j]);
-            gx[j] = geglu ? __uint_as_float(g[j]) : 0.f;
-          }
-          if (!complete) {
-            for (int f = f0; f <= f1; ++f) {
-              const float* wsf = p.ws + (long)f * (BN / CHUNK) * 128 * CHUNK;
-              const float4* src = reinterpret_cast<const float4*>(wsf + ((long)(c0 / CHUNK) * 128 + r) * CHUNK);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 t = __ldcg(src + q);
-                x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
-              }
-              if (geglu) {
+            for (int j = 0; j < CHUNK; ++j) {
+              x[j] = __uint_as_float(v[j]);
+              gx[j] = __uint_as_float(g[j]);
+            }
+            if (!complete) {
+              for (int f = f0; f <= f1; ++f) {
+                const float* wsf = p.ws + (long)f * (BN / CHUNK) * 128 * CHUNK;
+                const float4* src = reinterpret_cast<const float4*>(wsf + ((long)(c0 / CHUNK) * 128 + r) * CHUNK);
                 const float4* srcg = reinterpret_cast<const float4*>(
                     wsf + ((long)((BN / 2 + c0) / CHUNK) * 128 + r) * CHUNK);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  const float4 t = __ldcg(srcg + q);
-                  gx[4 * q] += t.x; gx[4 * q + 1] += t.y; gx[4 * q + 2] += t.z; gx[4 * q + 3] += t.w;
+                  const float4 t = __ldcg(src + q);
+                  const float4 u = __ldcg(srcg + q);
+                  x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+                  gx[4 * q] += u.x; gx[4 * q + 1] += u.y; gx[4 * q + 2] += u.z; gx[4 * q + 3] += u.w;
                 }
               }
             }
-          }
-          if (geglu) {
+            if (bias_t) {
 #pragma unroll
-            for (int j = 0; j < CHUNK; ++j) {
-              float val = x[j], gat = gx[j];
-              if (p.bias) {
-                val += __ldg(p.bias + n0 + c0 + j);
-                gat += __ldg(p.bias + n0 + BN / 2 + c0 + j);
+              for (int q = 0; q < 4; ++q) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_t + c0) + q);
+                const float4 bg = __ldg(reinterpret_cast<const float4*>(bias_t + BN / 2 + c0) + q);
+                x[4 * q] += bv.x; x[4 * q + 1] += bv.y; x[4 * q + 2] += bv.z; x[4 * q + 3] += bv.w;
+                gx[4 * q] += bg.x; gx[4 * q + 1] += bg.y; gx[4 * q + 2] += bg.z; gx[4 * q + 3] += bg.w;
               }
-              x[j] = val * gelu_erf_f(gat);
             }
-          } else {
 #pragma unroll
-            for (int j = 0; j < CHUNK; ++j) {
-              const int col = n0 + c0 + j;
-              float val = x[j];
-              if (col < p.N) {
-                if (p.bias) val += __ldg(p.bias + col);
-                if (p.rowadd && row_ok) val += __half2float(p.rowadd[(long)batch_idx * p.ldra + col]);
+            for (int j = 0; j < CHUNK; ++j) x[j] *= gelu_erf_f(gx[j]);
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) x[j] = __uint_as_float(v[j]);
+            if (!complete) {
+              for (int f = f0; f <= f1; ++f) {
+                const float* wsf = p.ws + (long)f * (BN / CHUNK) * 128 * CHUNK;
+                const float4* src = reinterpret_cast<const float4*>(wsf + ((long)(c0 / CHUNK) * 128 + r) * CHUNK);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 t = __ldcg(src + q);
+                  x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+                }
               }
-              if (do_silu) val = silu_f(val);
-              x[j] = val;
+            }
+            if (bias_t) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (q < 2 || hi_ok || nchw) {
+                  // nchw (N < 8 possible): bias vector may be shorter than a chunk -> scalar path below
+                  if (!nchw) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_t + c0) + q);
+                    x[4 * q] += bv.x; x[4 * q + 1] += bv.y; x[4 * q + 2] += bv.z; x[4 * q + 3] += bv.w;
+                  }
+                }
+              }
+              if (nchw) {
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j)
+                  if (n0 + c0 + j < p.N) x[j] += __ldg(bias_t + c0 + j);
+              }
+            }
+            if (radd_row && row_ok) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                if (q == 0 || hi_ok) {
+                  const uint4 rv = __ldg(reinterpret_cast<const uint4*>(radd_row + c0) + q);
+                  const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack_half2(ru[j]);
+                    x[8 * q + 2 * j] += f.x;
+                    x[8 * q + 2 * j + 1] += f.y;
+                  }
+                }
+              }
+            }
+            if (do_silu) {
+#pragma unroll
+              for (int j = 0; j < CHUNK; ++j) x[j] = silu_f(x[j]);
             }
           }
           if (row_ok) {
@@ -396,22 +443,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (col < n_out_total) o[((long)batch_idx * n_out_total + col) * hw + pix] = x[j];
               }
             } else {
-              __half* o = reinterpret_cast<__half*>(p.out) + out_row * p.ldo + out_c;
-              const __half* res = p.residual ? p.residual + out_row * p.ldr + out_c : nullptr;
 #pragma unroll
-              for (int j8 = 0; j8 < CHUNK / 8; ++j8) {
-                if (out_c + j8 * 8 < n_out_total) {
+              for (int q = 0; q < 2; ++q) {
+                if (q == 0 || hi_ok) {
                   float y[8];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) y[j] = x[j8 * 8 + j];
-                  if (res) {
-                    const uint4 rv = *reinterpret_cast<const uint4*>(res + j8 * 8);
+                  for (int j = 0; j < 8; ++j) y[j] = x[8 * q + j];
+                  if (res_row) {
+                    const uint4 rv = *(reinterpret_cast<const uint4*>(res_row + c0) + q);
                     const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                       const float2 f = unpack_half2(ru[j]);
-                      y[2 * j] = f.x + p.gate * y[2 * j];
-                      y[2 * j + 1] = f.y + p.gate * y[2 * j + 1];
+                      y[2 * j] = fmaf(gate, y[2 * j], f.x);
+                      y[2 * j + 1] = fmaf(gate, y[2 * j + 1], f.y);
                     }
                   }
                   uint4 ov;
@@ -419,7 +464,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   ov.y = pack_half2(y[2], y[3]);
                   ov.z = pack_half2(y[4], y[5]);
                   ov.w = pack_half2(y[6], y[7]);
-                  *reinterpret_cast<uint4*>(o + j8 * 8) = ov;
+                  *(reinterpret_cast<uint4*>(o_row + c0) + q) = ov;
                 }
               }
             }

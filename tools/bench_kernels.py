@@ -19,7 +19,7 @@ from instancediffusion_b200.packing import pack_geglu  # noqa: E402
 dev = torch.device("cuda:0")
 tag = sys.argv[1] if len(sys.argv) > 1 else "run"
 which = sys.argv[2] if len(sys.argv) > 2 else "all"
-flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+flush = torch.zeros(64 << 20, dtype=torch.int32, device=dev)  # 256 MB, read to evict L2 with clean lines
 B = 8
 
 
@@ -29,7 +29,8 @@ def timed(fn, iters=5):
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
-        flush.zero_()
+        flush.sum()  # read 256 MB: L2 now holds clean lines of `flush` only (a write-flush would leave
+        # 126 MB of dirty lines whose eviction is billed to the kernel under test)
         # keep the GPU busy (~150 us) while the CPU enqueues, so the events bracket pure device time
         torch.cuda._sleep(300000)
         s = torch.cuda.Event(enable_timing=True)
