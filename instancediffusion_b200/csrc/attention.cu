@@ -18,7 +18,13 @@
 #include "common.cuh"
 #include "host.cuh"
 
+#include <stdlib.h>
+
 namespace idiff {
+
+namespace att2 {
+int attention_v2_d40(const idiff_attn_args* a, cudaStream_t stream);  // attention2.cu
+}
 
 constexpr int ATT_THREADS = 192;
 constexpr int BQ = 128;
@@ -347,7 +353,15 @@ extern "C" int idiff_attention(const idiff_attn_args* a, void* stream) {
                 "idiff_attention: out must be 16B aligned, out_ld %% 8 == 0");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (a->head_dim) {
-    case 40: return launch_attention<40>(a, s);
+    case 40: {
+      // attention2.cu (two Q tiles, f16x2 exponentials, tensor-core row sums) is the production
+      // kernel for d=40; IDIFF_ATTN_V1=1 selects the first-generation kernel for A/B runs.
+      static const bool use_v1 = []() {
+        const char* e = getenv("IDIFF_ATTN_V1");
+        return e && e[0] == '1';
+      }();
+      return use_v1 ? launch_attention<40>(a, s) : att2::attention_v2_d40(a, s);
+    }
     case 80: return launch_attention<80>(a, s);
     case 160: return launch_attention<160>(a, s);
     default: return set_error("idiff_attention: unsupported head_dim %d (40/80/160)", a->head_dim);
