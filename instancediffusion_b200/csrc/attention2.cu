@@ -144,7 +144,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   // Register re-partition between warpgroups (the setmaxnreg must sit at the head of each role
   // branch so that ptxas allocates the branch bodies against the new limits).
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
