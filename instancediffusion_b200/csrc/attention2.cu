@@ -169,17 +169,35 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       constexpr uint32_t idesc_qk = make_idesc_f16(BQ, BKV, 0, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(BQ, C::DV, 0, 0, /*B MN-major*/ 1);
       constexpr uint32_t idesc_l = make_idesc_f16(BQ, 16, 0, 0, 0);
-      const uint32_t ones_base = smem_u32(sOnes);
+      // Every descriptor here shares its high word (SBO = 1024 B, version 1, SWIZZLE_128B); the low
+      // word is (address >> 4) | (LBO >> 4) << 16, so stepping an operand by X bytes is lo += X >> 4.
+      // The issuing thread therefore spends one integer add per UMMA (the tiles are small: N = 64 /
+      // 16 UMMAs last 32 / 8 clocks, so descriptor arithmetic in the issue loop would dominate).
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t LBO_K = (16u >> 4) << 16;             // K-major operands (unused field)
+      constexpr uint32_t LBO_V = ((BKV * 128u) >> 4) << 16;    // MN-major V: next 64-wide d chunk
+      const uint32_t q_lo0 = (smem_u32(sQ) >> 4) | LBO_K;
+      const uint32_t p_lo0 = (smem_u32(sP) >> 4) | LBO_K;
+      const uint32_t ones_lo = (smem_u32(sOnes) >> 4) | LBO_K;
+      const uint32_t k_lo0 = (smem_u32(sK) >> 4) | LBO_K;
+      const uint32_t v_lo0 = (smem_u32(sV) >> 4) | LBO_V;
+      auto umma_lo = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(d_tmem),
+            "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(acc)
+            : "memory");
+      };
       auto issue_qk = [&](int q, int j) {
-        const uint32_t q_base = smem_u32(sQ + q * C::Q_BYTES);
-        const uint32_t k_base = smem_u32(sK + (j % STAGES) * C::KV_BYTES);
+        const uint32_t q_lo = q_lo0 + q * (C::Q_BYTES >> 4);
+        const uint32_t k_lo = k_lo0 + (j % STAGES) * (C::KV_BYTES >> 4);
         const uint32_t d_tmem = tmem_base + (q ? C::S_COL1 : C::S_COL0);
 #pragma unroll
-        for (int kk = 0; kk < C::KSTEPS; ++kk) {
-          const uint64_t adesc = make_smem_desc_sw128(q_base + kk * 32, 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(k_base + kk * 32, 16, 1024);
-          umma_f16_ss(d_tmem, adesc, bdesc, idesc_qk, kk > 0 ? 1u : 0u);
-        }
+        for (int kk = 0; kk < C::KSTEPS; ++kk)
+          umma_lo(d_tmem, q_lo + kk * 2, k_lo + kk * 2, idesc_qk, kk > 0 ? 1u : 0u);
         umma_commit(&s_full[q]);
       };
       mbar_wait(q_full, 0);
@@ -198,22 +216,19 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
         }
         mbar_wait(&v_full[st], (j / STAGES) & 1);
-        const uint32_t v_base = smem_u32(sV + st * C::KV_BYTES);
+        const uint32_t v_lo = v_lo0 + st * (C::KV_BYTES >> 4);
         for (int q = 0; q < 2; ++q) {
           mbar_wait(&p_full[q], j & 1);
           tc_fence_after();
-          const uint32_t p_base = smem_u32(sP + q * C::P_BYTES);
+          const uint32_t p_lo = p_lo0 + q * (C::P_BYTES >> 4);
           const uint32_t o_tmem = tmem_base + (q ? C::O_COL1 : C::O_COL0);
           const uint32_t l_tmem = tmem_base + (q ? C::L_COL1 : C::L_COL0);
+          const uint32_t acc0 = j > 0 ? 1u : 0u;
 #pragma unroll
           for (int kk = 0; kk < BKV / 16; ++kk) {
-            const uint64_t adesc =
-                make_smem_desc_sw128(p_base + (kk >> 2) * (BQ * 128) + (kk & 3) * 32, 16, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(v_base + kk * 2048, BKV * 128, 1024);
-            umma_f16_ss(o_tmem, adesc, bdesc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-            const uint64_t odesc =
-                make_smem_desc_sw128(ones_base + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024);
-            umma_f16_ss(l_tmem, adesc, odesc, idesc_l, (j > 0 || kk > 0) ? 1u : 0u);
+            const uint32_t a_lo = p_lo + (kk >> 2) * ((BQ * 128) >> 4) + (kk & 3) * 2;
+            umma_lo(o_tmem, a_lo, v_lo + kk * (2048 >> 4), idesc_pv, kk > 0 ? 1u : acc0);
+            umma_lo(l_tmem, a_lo, ones_lo + (kk >> 2) * (2048 >> 4) + (kk & 3) * 2, idesc_l, kk > 0 ? 1u : acc0);
           }
           umma_commit(&pv_done[q]);
         }
