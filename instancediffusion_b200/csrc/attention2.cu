@@ -71,11 +71,10 @@ IDIFF_DEVICE void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
 }
 
 IDIFF_DEVICE uint32_t exp2_pack_h2(float x0, float x1) {
-  // {2^x0, 2^x1} as packed fp16: one cvt + one MUFU for two exponentials
-  __half2 h = __floats2half2_rn(x0, x1);
-  uint32_t u = *reinterpret_cast<uint32_t*>(&h), r;
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(u));
-  return r;
+  // {2^x0, 2^x1} as packed fp16.  ex2.approx.f16x2 was measured here first: on sm_100 it lowers to
+  // two scalar MUFU.EX2.F16 + a PRMT and ran at about half the fp32 MUFU rate (profiles/), so the
+  // exponentials stay fp32 MUFU.EX2 followed by one F2FP pack.
+  return pack_half2(exp2_approx(x0), exp2_approx(x1));
 }
 
 template <int D>
