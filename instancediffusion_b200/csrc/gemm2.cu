@@ -27,7 +27,7 @@ namespace v2 {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int THREADS = 320;
+constexpr int THREADS = 384;  // 3 warpgroups: {TMA, UMMA, 2 idle} + 2 x 4 epilogue warps
 constexpr int EPI_WARPS = 8;
 constexpr int CHUNK = 16;  // accumulator columns per tcgen05.ld
 
@@ -174,6 +174,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   };
 
+  // Warpgroup 0 = {TMA, UMMA, 2 idle warps} gives registers to the two epilogue warpgroups
+  // (setmaxnreg at the head of each role branch: 56*128 + 224*256 = the CTA's 168*384 allocation).
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -232,9 +236,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
     __syncwarp();
+  }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
-    const int ew = warp - 2;       // 0..7
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n");
+    // ===================== epilogue (warps 4..11) =====================
+    const int ew = warp - 4;       // 0..7
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int half = ew >> 2;      // which half of the tile's columns
     const int r = quarter * 32 + lane;
@@ -287,6 +293,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           pix = (int)(out_row - (long)batch_idx * p.rows_per_batch);
         }
       }
+      // Residual prefetch: the residual rows do not depend on the accumulator, so their loads are
+      // issued before the wait and overlap this segment's mainloop (the chunk loop below used to
+      // pay one exposed L2/HBM round trip per 16-column chunk: latency-, not bandwidth-bound).
+      const int out_col_base = geglu ? (sg.tile % p.n_tiles) * (BN / 2) : n0;
+      uint4 resv[NCH][2];
+      const bool has_res = owner && row_ok && p.residual != nullptr && !geglu;
+      if (has_res) {
+        const __half* res_row = p.residual + out_row * p.ldr + out_col_base;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int c0 = half * (BN / 2) + ch * CHUNK;
+          if (out_col_base + c0 < n_out_total) {
+            resv[ch][0] = *reinterpret_cast<const uint4*>(res_row + c0);
+            if (out_col_base + c0 + 8 < n_out_total) resv[ch][1] = *reinterpret_cast<const uint4*>(res_row + c0 + 8);
+          }
+        }
+      }
       mbar_wait(&tmem_full[acc], (sc >> 1) & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + acc * C::ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -308,7 +331,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
-        __threadfence();
+        // __syncwarp orders the lanes' partial stores before lane 0's release store (cumulative), so a
+        // single release replaces 32 per-thread __threadfence() (MEMBAR.GPU + L1 invalidate each).
         __syncwarp();
         if (lane == 0) st_release_gpu(p.sflags + cta * EPI_WARPS + ew, 1);
       } else {
@@ -330,14 +354,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // outside the per-element loops (the first version spent ~40 instructions per element on
         // address arithmetic and predicates and was issue-bound; see profiles/).
         const int nch = geglu ? NCH / 2 : NCH;  // GEGLU: the second half of the chunks are the gates
-        const int out_col_base = geglu ? (sg.tile % p.n_tiles) * (BN / 2) : n0;
         __half* o_row = reinterpret_cast<__half*>(p.out) + out_row * p.ldo + out_col_base;
-        const __half* res_row = p.residual ? p.residual + out_row * p.ldr + out_col_base : nullptr;
         const __half* radd_row = p.rowadd ? p.rowadd + (long)batch_idx * p.ldra + n0 : nullptr;
         const float* bias_t = p.bias ? p.bias + n0 : nullptr;
         const float gate = p.gate;
-#pragma unroll 1
-        for (int ch = 0; ch < nch; ++ch) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          if (ch >= nch) break;
           const int c0 = chunk_col(ch);  // accumulator column (value column in GEGLU mode)
           const int out_c = out_col_base + c0;
           if (out_c >= n_out_total) break;  // warp-uniform
@@ -449,8 +472,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   float y[8];
 #pragma unroll
                   for (int j = 0; j < 8; ++j) y[j] = x[8 * q + j];
-                  if (res_row) {
-                    const uint4 rv = *(reinterpret_cast<const uint4*>(res_row + c0) + q);
+                  if (has_res) {
+                    const uint4 rv = resv[ch][q];
                     const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {

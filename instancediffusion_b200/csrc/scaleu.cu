@@ -87,6 +87,18 @@ scaleu_coef_kernel(const uint4* __restrict__ skip, float* __restrict__ partial, 
   }
 }
 
+// partial [B][chunks][C][8] -> coef [B][C][8], fixed order (one thread per (b, c, q))
+__global__ void __launch_bounds__(256)
+scaleu_reduce_kernel(const float* __restrict__ partial, float* __restrict__ coef, int chunks, int C, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C * 8) return;
+  const int b = i / (C * 8);
+  const int rem = i - b * C * 8;
+  float a = 0.f;
+  for (int ch = 0; ch < chunks; ++ch) a += partial[((long)b * chunks + ch) * C * 8 + rem];
+  coef[i] = a;
+}
+
 // grid (chunks, B), block k*CVO, CVO = (C1+C2)/8
 __global__ void __launch_bounds__(512)
 scaleu_apply_kernel(const uint4* __restrict__ h, const uint4* __restrict__ skip, uint4* __restrict__ out,
@@ -180,7 +192,7 @@ static void su_geometry(int batch, int hw, int cv, int max_chunks, int* k, int* 
 }  // namespace idiff
 
 extern "C" long idiff_scaleu_ws_floats(int batch, int c2) {
-  return (long)batch * idiff::SU_MAX_CHUNKS * c2 * 8;
+  return (long)batch * (idiff::SU_MAX_CHUNKS + 1) * c2 * 8;  // per-chunk partials + the reduced coefficients
 }
 
 extern "C" int idiff_scaleu_concat(const void* h, const void* skip, void* out, const float* b1, float s,
@@ -204,11 +216,13 @@ extern "C" int idiff_scaleu_concat(const void* h, const void* skip, void* out, c
   IDIFF_REQUIRE(smem <= 160 * 1024, "idiff_scaleu_concat: shared memory %zu too large", smem);
   scaleu_coef_kernel<<<dim3(chunks1, batch), k1 * (c2 / 8), smem, st>>>(reinterpret_cast<const uint4*>(skip), coef_ws,
                                                                        height, width, c2, ppb1, k1);
+  float* coef = coef_ws + (long)batch * SU_MAX_CHUNKS * c2 * 8;
+  scaleu_reduce_kernel<<<(batch * c2 * 8 + 255) / 256, 256, 0, st>>>(coef_ws, coef, chunks1, c2, batch);
   int k2, ppb2, chunks2;
   su_geometry(batch, hw, (c1 + c2) / 8, 4096, &k2, &ppb2, &chunks2);
   scaleu_apply_kernel<<<dim3(chunks2, batch), k2 * ((c1 + c2) / 8), 0, st>>>(
       reinterpret_cast<const uint4*>(h), reinterpret_cast<const uint4*>(skip), reinterpret_cast<uint4*>(out), b1,
-      coef_ws, s - 1.0f, height, width, c1, c2, ppb2, k2, chunks1);
+      coef, s - 1.0f, height, width, c1, c2, ppb2, k2, 1);
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -317,6 +317,7 @@ class UNetModel(PackedModule):
         self._ctx_cache: Dict = {}
         self._obj_cache: Dict = {}
         self._graphs: Dict = {}
+        self._in_packs: Dict = {}
         self.use_cuda_graph = os.environ.get("IDIFF_CUDA_GRAPH", "1") != "0"
 
     # ------------------------------------------------------------------------------------------
@@ -350,8 +351,14 @@ class UNetModel(PackedModule):
         new.load_state_dict(sd_weights)
         self.input_blocks[0][0] = new.to(device)
         self._first_conv_restored = True
-        self._pk = None
-        self._graphs.clear()
+        # The packed first-conv weights of both states are kept alive side by side (the captured CUDA
+        # graphs of either state point at them), so swapping costs nothing and invalidates nothing --
+        # unless different SD weights than last time are supplied.
+        if getattr(self, "_sd_conv_src", None) is not sd_weights:
+            self._sd_conv_src = sd_weights
+            self._in_packs.pop(True, None)
+            for k in [k for k in self._graphs if k[-1]]:
+                del self._graphs[k]
 
     def undo_first_conv_restore(self):
         """Not in the reference (whose swap is permanent within a process): lets a long-lived server /
@@ -359,8 +366,28 @@ class UNetModel(PackedModule):
         if getattr(self, "_first_conv_restored", False):
             self.input_blocks[0][0].load_state_dict(self.first_conv_state_dict)
             self._first_conv_restored = False
-            self._pk = None
+
+    def _in_conv_pack(self):
+        key = bool(getattr(self, "_first_conv_restored", False))
+        hit = self._in_packs.get(key)
+        if hit is None:
+            conv0 = self.input_blocks[0][0]
+            with torch.no_grad():
+                hit = (_pack_conv3x3_padded(conv0.weight, 64), f32(conv0.bias))
+            self._in_packs[key] = hit
+        return hit
+
+    def _apply(self, fn, *a, **k):
+        if hasattr(self, "_in_packs"):
+            self._in_packs.clear()
             self._graphs.clear()
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        if hasattr(self, "_in_packs"):
+            self._in_packs.clear()
+            self._graphs.clear()
+        return super()._load_from_state_dict(*a, **k)
 
     # ------------------------------------------------------------------------------------------
     # packing
@@ -372,9 +399,7 @@ class UNetModel(PackedModule):
         return [m for m in self.modules() if isinstance(m, SpatialTransformer)]
 
     def _pack(self):
-        conv0 = self.input_blocks[0][0]
         p = {
-            "w_in": _pack_conv3x3_padded(conv0.weight, 64), "b_in": f32(conv0.bias),
             "wt0": w16(self.time_embed[0].weight), "bt0": f32(self.time_embed[0].bias),
             "wt2": w16(self.time_embed[2].weight), "bt2": f32(self.time_embed[2].bias),
             "g_out": f32(self.out[0].weight), "b_out": f32(self.out[0].bias),
@@ -503,7 +528,8 @@ class UNetModel(PackedModule):
             return h, hh, ww
 
         x16 = ops.nchw_f32_to_nhwc_f16(x, 64)
-        h = ops.gemm(x16, p["w_in"], p["b_in"], conv=(B, H, W, 64))
+        w_in, b_in = self._in_conv_pack()
+        h = ops.gemm(x16, w_in, b_in, conv=(B, H, W, 64))
         hh, ww = H, W
         hs = [(h, hh, ww)]
         for module in list(self.input_blocks)[1:]:

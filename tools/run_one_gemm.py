@@ -25,6 +25,9 @@ elif which == "geglu320":
     a, w, b = r(B * 4096, 320), r(2560, 320, sc=0.05), torch.randn(2560, device=dev)
     wp, bp = pack_geglu(w, b)
     fn = lambda: ops.gemm(a, wp, bp, geglu=True)
+elif which == "proj1280":
+    a, w, res, b = r(B * 256, 1280), r(1280, 1280, sc=0.03), r(B * 256, 1280), torch.randn(1280, device=dev)
+    fn = lambda: ops.gemm(a, w, b, residual=res)
 elif which == "conv320":
     a, w, b, res = r(B * 4096, 320), r(320, 2880, sc=0.02), torch.randn(320, device=dev), r(B * 4096, 320)
     fn = lambda: ops.gemm(a, w, b, conv=(B, 64, 64, 320), residual=res)
