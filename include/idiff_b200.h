@@ -67,6 +67,9 @@ int idiff_gemm(const idiff_gemm_args* args, void* stream);
  * not share it. */
 long idiff_gemm_workspace_bytes(void);
 int idiff_set_gemm_workspace(void* ptr, long bytes);
+/* Profiling hook: device buffer of 8 x uint64 per CTA (>= 148*8) receiving %globaltimer stamps of
+ * each GEMM CTA's phases; NULL (default) disables it. */
+int idiff_set_gemm_trace(void* ptr);
 
 /* ---------------------------------------------------------------------------------------------
  * idiff_attention: softmax(Q K^T * scale) V per (batch, head), flash-style online softmax with

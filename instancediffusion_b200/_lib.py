@@ -51,6 +51,7 @@ SIGNATURES = {
     "idiff_gemm": (_i, [C.POINTER(GemmArgs), _vp]),
     "idiff_gemm_workspace_bytes": (_l, []),
     "idiff_set_gemm_workspace": (_i, [_vp, _l]),
+    "idiff_set_gemm_trace": (_i, [_vp]),
     "idiff_attention": (_i, [C.POINTER(AttnArgs), _vp]),
     "idiff_groupnorm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     "idiff_groupnorm_ws_floats": (_l, [_i, _i]),

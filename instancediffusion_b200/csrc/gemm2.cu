@@ -47,6 +47,7 @@ struct Params {
   // stream-K fixup
   float* ws;    // [G][BN/CHUNK][128][CHUNK] fp32 partial tiles
   int* sflags;  // [G][EPI_WARPS] publish flags (fixed location, self-resetting)
+  unsigned long long* trace;  // optional [G][8] %globaltimer stamps (idiff_set_gemm_trace), else null
 };
 
 template <int BN>
@@ -157,6 +158,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  auto stamp = [&](int slot) {
+    if (p.trace) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.trace[(long)cta * 8 + slot] = t;
+    }
+  };
+  if (threadIdx.x == 0) stamp(0);
 
   auto tile_origin = [&](int tile, int& n0, int& m0, int& b0, int& h0, int& w0) {
     const int n_tile = tile % p.n_tiles;
@@ -220,6 +229,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++kc) {
           const int s = kc % STAGES;
           mbar_wait(&full_bar[s], (kc / STAGES) & 1);
+          if (kc == 0) stamp(1);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + s * A_STAGE_BYTES);
           const uint32_t b_base = smem_u32(sB + s * C::B_STAGE_BYTES);
@@ -232,6 +242,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full[acc]);
+        if (sc == 0) stamp(2);
         ++sc;
       }
     }
@@ -311,6 +322,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
       mbar_wait(&tmem_full[acc], (sc >> 1) & 1);
+      if (sc == 0 && threadIdx.x == 128) stamp(3);
       tc_fence_after();
       const uint32_t trow = tmem_base + acc * C::ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
 
@@ -353,6 +365,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // 16-byte vector loads per 16-column chunk, and mode switches are warp-uniform branches
         // outside the per-element loops (the first version spent ~40 instructions per element on
         // address arithmetic and predicates and was issue-bound; see profiles/).
+        if (sc == 0 && threadIdx.x == 128) stamp(4);
         const int nch = geglu ? NCH / 2 : NCH;  // GEGLU: the second half of the chunks are the gates
         __half* o_row = reinterpret_cast<__half*>(p.out) + out_row * p.ldo + out_col_base;
         const __half* radd_row = p.rowadd ? p.rowadd + (long)batch_idx * p.ldra + n0 : nullptr;
@@ -493,6 +506,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
         }
+        if (sc == 0 && threadIdx.x == 128) stamp(5);
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
         if (!complete) {
@@ -506,7 +520,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   }
 
+  if (threadIdx.x == 128) stamp(6);
   __syncthreads();
+  if (threadIdx.x == 0) stamp(7);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<C::TMEM_COLS>(tmem_base);
@@ -517,6 +533,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // host side
 // ---------------------------------------------------------------------------------------------
 static void* g_ws = nullptr;
+static unsigned long long* g_trace = nullptr;
 static long g_ws_bytes = 0;
 static int g_num_sms = 0;
 constexpr long kFlagBytes = 64 * 1024;
@@ -566,6 +583,7 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream) {
   p.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : a->M;
   p.flags = a->flags;
   p.gate = a->gate;
+  p.trace = g_trace;
 
   CUtensorMap tmA, tmB;
   int m_tiles;
@@ -661,6 +679,14 @@ extern "C" int idiff_set_gemm_workspace(void* ptr, long bytes) {
   }
   v2::g_ws = ptr;
   v2::g_ws_bytes = ptr ? bytes : 0;
+  return 0;
+}
+
+// Debug / profiling hook: when set, every GEMM CTA writes 8 %globaltimer stamps (kernel entry,
+// first operand tile landed, first segment issued, first accumulator ready, fixup done, first
+// epilogue done, role loops done, exit) to trace[cta*8 ..].  Pass NULL to disable (default).
+extern "C" int idiff_set_gemm_trace(void* ptr) {
+  idiff::v2::g_trace = reinterpret_cast<unsigned long long*>(ptr);
   return 0;
 }
 
