@@ -30,6 +30,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int THREADS = 384;  // 3 warpgroups: {TMA, UMMA, 2 idle} + 2 x 4 epilogue warps
 constexpr int EPI_WARPS = 8;
 constexpr int CHUNK = 16;  // accumulator columns per tcgen05.ld
+constexpr int EPI_TAB_PB = 4;  // batches a conv tile may straddle and still use the smem epilogue table
 
 struct Params {
   int M, N, K, KB;
@@ -57,7 +58,7 @@ struct Cfg {
   static constexpr int STAGES = (BN <= 128) ? 6 : ((BN <= 192) ? 5 : 4);
   static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 2 * EPI_TAB_PB * BN * 4;
 };
 
 struct Seg {
@@ -135,6 +136,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* s_epi = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES + 256);  // [2][EPI_TAB_PB][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -321,6 +323,28 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
       }
+      // Per-tile epilogue table in shared memory: tab[pb][c] = bias[n0+c] (+ rowadd[b0+pb][n0+c]), so
+      // the chunk loop adds its per-column terms with broadcast LDS instead of one exposed L2 round
+      // trip per chunk (measured ~1 us per 16-column chunk before; tools/trace_gemm.py).
+      const bool tab_rowadd = p.rowadd != nullptr && p.conv && p.PB <= EPI_TAB_PB;
+      const bool slow_rowadd = p.rowadd != nullptr && !tab_rowadd;
+      float* tab = s_epi + acc * (EPI_TAB_PB * BN);
+      if (owner) {
+        const int npb = tab_rowadd ? p.PB : 1;
+        const int et = threadIdx.x - 128;  // 0..255
+        for (int idx = et; idx < npb * BN; idx += EPI_WARPS * 32) {
+          const int pb = idx / BN, c = idx - pb * BN;
+          const int col = n0 + c;
+          float val = 0.f;
+          if (col < p.N) {
+            if (p.bias) val = __ldg(p.bias + col);
+            if (tab_rowadd && b0 + pb < p.Bn) val += __half2float(p.rowadd[(long)(b0 + pb) * p.ldra + col]);
+          }
+          tab[idx] = val;
+        }
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      }
+      const float* tab_row = tab + ((tab_rowadd && p.conv) ? (r / (p.PW * p.PH)) * BN : 0);
       mbar_wait(&tmem_full[acc], (sc >> 1) & 1);
       if (sc == 0 && threadIdx.x == 128) stamp(3);
       tc_fence_after();
@@ -369,8 +393,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int nch = geglu ? NCH / 2 : NCH;  // GEGLU: the second half of the chunks are the gates
         __half* o_row = reinterpret_cast<__half*>(p.out) + out_row * p.ldo + out_col_base;
         const __half* radd_row = p.rowadd ? p.rowadd + (long)batch_idx * p.ldra + n0 : nullptr;
-        const float* bias_t = p.bias ? p.bias + n0 : nullptr;
         const float gate = p.gate;
+        float4 pnext[4];
+        if (!complete && !geglu) {
+          const float* ws0 = p.ws + (long)f0 * (BN / CHUNK) * 128 * CHUNK;
+          const float4* src0 = reinterpret_cast<const float4*>(
+              ws0 + ((long)((half * (BN / 2)) / CHUNK) * 128 + r) * CHUNK);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) pnext[q] = __ldcg(src0 + q);
+        }
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
           if (ch >= nch) break;
@@ -406,14 +437,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 }
               }
             }
-            if (bias_t) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_t + c0) + q);
-                const float4 bg = __ldg(reinterpret_cast<const float4*>(bias_t + BN / 2 + c0) + q);
-                x[4 * q] += bv.x; x[4 * q + 1] += bv.y; x[4 * q + 2] += bv.z; x[4 * q + 3] += bv.w;
-                gx[4 * q] += bg.x; gx[4 * q + 1] += bg.y; gx[4 * q + 2] += bg.z; gx[4 * q + 3] += bg.w;
-              }
+            for (int q = 0; q < 4; ++q) {
+              const float4 bv = *(reinterpret_cast<const float4*>(tab_row + c0) + q);
+              const float4 bg = *(reinterpret_cast<const float4*>(tab_row + BN / 2 + c0) + q);
+              x[4 * q] += bv.x; x[4 * q + 1] += bv.y; x[4 * q + 2] += bv.z; x[4 * q + 3] += bv.w;
+              gx[4 * q] += bg.x; gx[4 * q + 1] += bg.y; gx[4 * q + 2] += bg.z; gx[4 * q + 3] += bg.w;
             }
 #pragma unroll
             for (int j = 0; j < CHUNK; ++j) x[j] *= gelu_erf_f(gx[j]);
@@ -422,7 +451,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < CHUNK; ++j) x[j] = __uint_as_float(v[j]);
             if (!complete) {
-              for (int f = f0; f <= f1; ++f) {
+              // stream-K fixup: the first follower's partial of this chunk was requested one chunk
+              // earlier (pnext), the request for the next chunk goes out before this one is consumed
+              float4 pcur[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) pcur[q] = pnext[q];
+              if (ch + 1 < NCH) {
+                const float* wsn = p.ws + (long)f0 * (BN / CHUNK) * 128 * CHUNK;
+                const float4* srcn = reinterpret_cast<const float4*>(
+                    wsn + ((long)((c0 + CHUNK) / CHUNK) * 128 + r) * CHUNK);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pnext[q] = __ldcg(srcn + q);
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                x[4 * q] += pcur[q].x; x[4 * q + 1] += pcur[q].y; x[4 * q + 2] += pcur[q].z; x[4 * q + 3] += pcur[q].w;
+              }
+              for (int f = f0 + 1; f <= f1; ++f) {
                 const float* wsf = p.ws + (long)f * (BN / CHUNK) * 128 * CHUNK;
                 const float4* src = reinterpret_cast<const float4*>(wsf + ((long)(c0 / CHUNK) * 128 + r) * CHUNK);
 #pragma unroll
@@ -432,24 +477,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 }
               }
             }
-            if (bias_t) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (q < 2 || hi_ok || nchw) {
-                  // nchw (N < 8 possible): bias vector may be shorter than a chunk -> scalar path below
-                  if (!nchw) {
-                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_t + c0) + q);
-                    x[4 * q] += bv.x; x[4 * q + 1] += bv.y; x[4 * q + 2] += bv.z; x[4 * q + 3] += bv.w;
-                  }
-                }
-              }
-              if (nchw) {
-#pragma unroll
-                for (int j = 0; j < CHUNK; ++j)
-                  if (n0 + c0 + j < p.N) x[j] += __ldg(bias_t + c0 + j);
-              }
+            for (int q = 0; q < 4; ++q) {
+              const float4 bv = *(reinterpret_cast<const float4*>(tab_row + c0) + q);
+              x[4 * q] += bv.x; x[4 * q + 1] += bv.y; x[4 * q + 2] += bv.z; x[4 * q + 3] += bv.w;
             }
-            if (radd_row && row_ok) {
+            if (slow_rowadd && row_ok) {
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
                 if (q == 0 || hi_ok) {
