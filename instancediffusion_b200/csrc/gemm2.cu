@@ -119,7 +119,11 @@ IDIFF_DEVICE void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int BN>
+constexpr int MODE_PLAIN = 0;  // bias / row-add table, optional SiLU, optional gate*x + residual, fp16 out
+constexpr int MODE_GEGLU = 1;  // (value + b) * gelu(gate + b), fp16 out with N/2 columns
+constexpr int MODE_NCHW = 2;   // fp32 (B, N, HW) output (the final conv -> eps)
+
+template <int BN, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const Params p) {
@@ -257,9 +261,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int half = ew >> 2;      // which half of the tile's columns
     const int r = quarter * 32 + lane;
-    const bool geglu = (p.flags & IDIFF_EPI_GEGLU) != 0;
+    constexpr bool geglu = (MODE == MODE_GEGLU);
+    constexpr bool nchw = (MODE == MODE_NCHW);
     const bool do_silu = (p.flags & IDIFF_EPI_SILU) != 0;
-    const bool nchw = (p.flags & IDIFF_OUT_F32_NCHW) != 0;
     const int n_out_total = geglu ? p.N / 2 : p.N;
     constexpr int NCH = BN / 2 / CHUNK;  // accumulator chunks owned by this warp
     // Accumulator column of chunk `ch` of this warp.  Plain: a contiguous half of the tile.
@@ -597,7 +601,7 @@ static int pick_bn(int N, bool geglu) {
   return best;
 }
 
-template <int BN>
+template <int BN, int MODE>
 static int launch(const idiff_gemm_args* a, cudaStream_t stream) {
   using C = Cfg<BN>;
   Params p;
@@ -681,22 +685,26 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           C::SMEM_BYTES));
     attr_set = true;
   }
-  gemm2_kernel<BN><<<p.G, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm2_kernel<BN, MODE><<<p.G, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
+// One instantiation per (tile width, epilogue mode): the epilogue is fully unrolled over its
+// column chunks, so each kernel carries only its own mode's code (an all-modes kernel was ~140 KB
+// of SASS and stalled on instruction fetch: 26 % stall_no_inst, profiles/).
 int gemm_v2(const idiff_gemm_args* a, cudaStream_t stream) {
-  const bool geglu = (a->flags & IDIFF_EPI_GEGLU) != 0;
-  switch (pick_bn(a->N, geglu)) {
-    case 256: return launch<256>(a, stream);
-    case 192: return launch<192>(a, stream);
-    case 160: return launch<160>(a, stream);
-    default: return launch<128>(a, stream);
+  if (a->flags & IDIFF_EPI_GEGLU) return launch<128, MODE_GEGLU>(a, stream);
+  if (a->flags & IDIFF_OUT_F32_NCHW) return launch<128, MODE_NCHW>(a, stream);
+  switch (pick_bn(a->N, false)) {
+    case 256: return launch<256, MODE_PLAIN>(a, stream);
+    case 192: return launch<192, MODE_PLAIN>(a, stream);
+    case 160: return launch<160, MODE_PLAIN>(a, stream);
+    default: return launch<128, MODE_PLAIN>(a, stream);
   }
 }
 
