@@ -51,14 +51,25 @@ struct Params {
   unsigned long long* trace;  // optional [G][8] %globaltimer stamps (idiff_set_gemm_trace), else null
 };
 
-template <int BN>
+// TMA_EPI: the epilogue moves the residual in and the result out through shared memory with
+// bulk-tensor copies ([32 rows x 16 cols] boxes, one per warp and 16-column chunk) instead of one
+// 16-byte global access per thread and row (which costs an L1 transaction per access: measured
+// ~0.7 us per chunk, tools/trace_gemm.py).  The staging buffer takes smem from the operand ring,
+// so it is used for the short-K layers (epilogue-bound); long-K convolutions keep the deep ring.
+template <int BN, bool TMA_EPI>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN <= 128) ? 6 : ((BN <= 192) ? 5 : 4);
+  static constexpr int BOX_BYTES = 32 * CHUNK * 2;                       // 1 KiB
+  static constexpr int STG_BYTES = TMA_EPI ? EPI_WARPS * (BN / 2 / CHUNK) * BOX_BYTES : 0;
+  static constexpr int TAB_BYTES = 2 * EPI_TAB_PB * BN * 4;
+  static constexpr int FIXED = 1024 + 256 + TAB_BYTES + STG_BYTES;
+  static constexpr int STAGES_FIT = (227 * 1024 - FIXED) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 2 * EPI_TAB_PB * BN * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
+  static_assert(STAGES >= 3, "operand ring too shallow");
 };
 
 struct Seg {
@@ -123,11 +134,12 @@ constexpr int MODE_PLAIN = 0;  // bias / row-add table, optional SiLU, optional 
 constexpr int MODE_GEGLU = 1;  // (value + b) * gelu(gate + b), fp16 out with N/2 columns
 constexpr int MODE_NCHW = 2;   // fp32 (B, N, HW) output (the final conv -> eps)
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool TMA_EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
              const Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, TMA_EPI>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -139,8 +151,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* res_bar = bars + 2 * STAGES + 4;     // [EPI_WARPS] residual boxes landed (TMA_EPI)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + EPI_WARPS);
   float* s_epi = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES + 256);  // [2][EPI_TAB_PB][BN]
+  uint8_t* s_stage = smem + STAGES * C::STAGE_BYTES + 256 + C::TAB_BYTES;          // [EPI_WARPS][NCH][1 KiB]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -156,6 +170,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], EPI_WARPS * 32);
+    }
+    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&res_bar[w], 1);
+    if (TMA_EPI) {
+      tma_prefetch_desc(&tmO);
+      tma_prefetch_desc(&tmR);
     }
     fence_barrier_init();
   }
@@ -277,6 +296,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     WorkIter it(p, cta);
     Seg sg;
     uint32_t sc = 0;
+    uint32_t res_phase = 0;  // parity of this warp's residual-landed barrier
     while (it.next(sg)) {
       const int acc = sc & 1;
       int n0, m0, b0, h0, w0;
@@ -314,9 +334,43 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // issued before the wait and overlap this segment's mainloop (the chunk loop below used to
       // pay one exposed L2/HBM round trip per 16-column chunk: latency-, not bandwidth-bound).
       const int out_col_base = geglu ? (sg.tile % p.n_tiles) * (BN / 2) : n0;
-      uint4 resv[NCH][2];
-      const bool has_res = owner && row_ok && p.residual != nullptr && !geglu;
-      if (has_res) {
+      uint4 resv[TMA_EPI ? 1 : NCH][2];
+      const bool has_res = owner && (TMA_EPI || row_ok) && p.residual != nullptr && !geglu;
+      // staging boxes of this warp: box ch holds rows [32*quarter, +32) x 16 output columns
+      uint8_t* wstage = s_stage + (TMA_EPI ? ew * (NCH * C::BOX_BYTES) : 0);
+      // tile-local coordinates of this warp's first row, for the output / residual tensor maps
+      int tc1 = 0, tc2 = 0, tc3 = 0;
+      if (TMA_EPI && owner) {
+        if (p.conv) {
+          const int r0 = quarter * 32;
+          const int pb = r0 / (p.PW * p.PH);
+          const int rem = r0 - pb * (p.PW * p.PH);
+          tc1 = w0 + rem % p.PW;
+          tc2 = h0 + rem / p.PW;
+          tc3 = b0 + pb;
+        } else {
+          tc1 = m0 + quarter * 32;
+        }
+        // the previous tile's stores must have finished reading the boxes before they are refilled
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        if (has_res && lane == 0) {
+          int nbox = 0;
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch)
+            if (out_col_base + half * (BN / 2) + ch * CHUNK < n_out_total) ++nbox;
+          mbar_expect_tx(&res_bar[ew], nbox * C::BOX_BYTES);
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            const int col = out_col_base + half * (BN / 2) + ch * CHUNK;
+            if (col < n_out_total) {
+              if (p.conv) tma_load_4d(wstage + ch * C::BOX_BYTES, &tmR, &res_bar[ew], col, tc1, tc2, tc3);
+              else tma_load_2d(wstage + ch * C::BOX_BYTES, &tmR, &res_bar[ew], col, tc1);
+            }
+          }
+        }
+      }
+      if (!TMA_EPI && has_res) {
         const __half* res_row = p.residual + out_row * p.ldr + out_col_base;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
@@ -394,6 +448,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // outside the per-element loops (the first version spent ~40 instructions per element on
         // address arithmetic and predicates and was issue-bound; see profiles/).
         if (sc == 0 && threadIdx.x == 128) stamp(4);
+        if (TMA_EPI && has_res) {
+          mbar_wait(&res_bar[ew], res_phase);
+          res_phase ^= 1;
+        }
         const int nch = geglu ? NCH / 2 : NCH;  // GEGLU: the second half of the chunks are the gates
         __half* o_row = reinterpret_cast<__half*>(p.out) + out_row * p.ldo + out_col_base;
         const __half* radd_row = p.rowadd ? p.rowadd + (long)batch_idx * p.ldra + n0 : nullptr;
@@ -515,6 +573,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const int col = out_c + j;
                 if (col < n_out_total) o[((long)batch_idx * n_out_total + col) * hw + pix] = x[j];
               }
+            } else if (TMA_EPI) {
+              // unreachable: TMA_EPI handles the store below (outside the row_ok guard)
             } else {
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
@@ -523,7 +583,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
                   for (int j = 0; j < 8; ++j) y[j] = x[8 * q + j];
                   if (has_res) {
-                    const uint4 rv = resv[ch][q];
+                    const uint4 rv = resv[TMA_EPI ? 0 : ch][q];
                     const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -542,7 +602,44 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
             }
           }
+          if (TMA_EPI && !nchw) {
+            // box `ch`: row `lane` is 32 B; SWIZZLE_32B puts 16-byte chunk q at (q ^ ((lane >> 2) & 1)).
+            // The residual (if any) was landed here by TMA; the result replaces it in place and one
+            // elected lane sends the box out.  Rows / columns outside the tensor are clipped by TMA.
+            uint8_t* box = wstage + ch * C::BOX_BYTES + lane * 32;
+            const int swz = (lane >> 2) & 1;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              uint4* slot = reinterpret_cast<uint4*>(box + ((q ^ swz) << 4));
+              float y[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y[j] = x[8 * q + j];
+              if (has_res) {
+                const uint4 rv = *slot;
+                const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = unpack_half2(ru[j]);
+                  y[2 * j] = fmaf(gate, y[2 * j], f.x);
+                  y[2 * j + 1] = fmaf(gate, y[2 * j + 1], f.y);
+                }
+              }
+              uint4 ov;
+              ov.x = pack_half2(y[0], y[1]);
+              ov.y = pack_half2(y[2], y[3]);
+              ov.z = pack_half2(y[4], y[5]);
+              ov.w = pack_half2(y[6], y[7]);
+              *slot = ov;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.conv) tma_store_4d(&tmO, wstage + ch * C::BOX_BYTES, out_c, tc1, tc2, tc3);
+              else tma_store_2d(&tmO, wstage + ch * C::BOX_BYTES, out_c, tc1);
+            }
+          }
         }
+        if (TMA_EPI && lane == 0) tma_store_commit();
         if (sc == 0 && threadIdx.x == 128) stamp(5);
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
@@ -557,6 +654,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   }
 
+  if (TMA_EPI && warp >= 4 && lane == 0) tma_store_wait_read();  // boxes must outlive their stores
   if (threadIdx.x == 128) stamp(6);
   __syncthreads();
   if (threadIdx.x == 0) stamp(7);
@@ -574,6 +672,10 @@ static unsigned long long* g_trace = nullptr;
 static long g_ws_bytes = 0;
 static int g_num_sms = 0;
 constexpr long kFlagBytes = 64 * 1024;
+static int kTmaEpiMaxKB = []() {
+  const char* e = getenv("IDIFF_TMA_EPI_MAX_KB");  // tuning knob: k-blocks up to which the TMA epilogue is used
+  return e ? atoi(e) : 40;
+}();
 
 static void choose_patch(int H, int W, int* PW, int* PH, int* PB) {
   int pw = 1;
@@ -601,9 +703,9 @@ static int pick_bn(int N, bool geglu) {
   return best;
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool TMA_EPI>
 static int launch(const idiff_gemm_args* a, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, TMA_EPI>;
   Params p;
   memset(&p, 0, sizeof(p));
   p.M = a->M;
@@ -683,13 +785,34 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream) {
     p.U_sk = 0;
   }
 
+  // output / residual views for the TMA epilogue: [32 rows x 16 cols] boxes, SWIZZLE_32B
+  CUtensorMap tmO = tmA, tmR = tmA;
+  if (TMA_EPI) {
+    const int n_out = (MODE == MODE_GEGLU) ? a->N / 2 : a->N;
+    auto make = [&](CUtensorMap* m, const void* base, int ld) -> int {
+      if (p.conv) {
+        const int pws = p.PW < 32 ? p.PW : 32;
+        const uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Bn};
+        const uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)p.W * ld * 2, (uint64_t)p.H * p.W * ld * 2};
+        const uint32_t box[4] = {(uint32_t)CHUNK, (uint32_t)pws, (uint32_t)(32 / pws), 1u};
+        return encode_tmap_f16_sw(m, base, 4, dims, strides, box, 32);
+      }
+      const uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)a->M};
+      const uint64_t strides[1] = {(uint64_t)ld * 2};
+      const uint32_t box[2] = {(uint32_t)CHUNK, 32u};
+      return encode_tmap_f16_sw(m, base, 2, dims, strides, box, 32);
+    };
+    if (make(&tmO, a->out, a->ldo)) return -1;
+    if (a->residual && make(&tmR, a->residual, a->ldr)) return -1;
+  }
+
   static bool attr_set = false;
   if (!attr_set) {
-    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          C::SMEM_BYTES));
+    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MODE, TMA_EPI>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  gemm2_kernel<BN, MODE><<<p.G, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm2_kernel<BN, MODE, TMA_EPI><<<p.G, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmR, p);
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -698,13 +821,16 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream) {
 // column chunks, so each kernel carries only its own mode's code (an all-modes kernel was ~140 KB
 // of SASS and stalled on instruction fetch: 26 % stall_no_inst, profiles/).
 int gemm_v2(const idiff_gemm_args* a, cudaStream_t stream) {
-  if (a->flags & IDIFF_EPI_GEGLU) return launch<128, MODE_GEGLU>(a, stream);
-  if (a->flags & IDIFF_OUT_F32_NCHW) return launch<128, MODE_NCHW>(a, stream);
+  if (a->flags & IDIFF_EPI_GEGLU) return launch<128, MODE_GEGLU, true>(a, stream);
+  if (a->flags & IDIFF_OUT_F32_NCHW) return launch<128, MODE_NCHW, false>(a, stream);
+  // short K: the epilogue dominates -> TMA-staged epilogue (shallower operand ring);
+  // long K (3x3 convolutions): deep operand ring, direct epilogue hidden behind the next mainloop
+  const bool tma_epi = ((a->K + BK - 1) / BK) <= kTmaEpiMaxKB;
   switch (pick_bn(a->N, false)) {
-    case 256: return launch<256, MODE_PLAIN>(a, stream);
-    case 192: return launch<192, MODE_PLAIN>(a, stream);
-    case 160: return launch<160, MODE_PLAIN>(a, stream);
-    default: return launch<128, MODE_PLAIN>(a, stream);
+    case 256: return tma_epi ? launch<256, MODE_PLAIN, true>(a, stream) : launch<256, MODE_PLAIN, false>(a, stream);
+    case 192: return tma_epi ? launch<192, MODE_PLAIN, true>(a, stream) : launch<192, MODE_PLAIN, false>(a, stream);
+    case 160: return tma_epi ? launch<160, MODE_PLAIN, true>(a, stream) : launch<160, MODE_PLAIN, false>(a, stream);
+    default: return tma_epi ? launch<128, MODE_PLAIN, true>(a, stream) : launch<128, MODE_PLAIN, false>(a, stream);
   }
 }
 

@@ -27,5 +27,8 @@ int set_error(const char* fmt, ...);  // always returns -1
 // dims/strides innermost-first; strides[i] (bytes) is the stride of dim i+1 (rank-1 entries).
 int encode_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box);
+// same with an explicit swizzle span (128 / 64 / 32 bytes, 0 = none)
+int encode_tmap_f16_sw(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 }  // namespace idiff
