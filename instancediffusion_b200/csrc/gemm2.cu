@@ -187,7 +187,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (p.trace) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      p.trace[(long)cta * 8 + slot] = t;
+      p.trace[(long)cta * 16 + slot] = t;
     }
   };
   if (threadIdx.x == 0) stamp(0);
@@ -452,136 +452,156 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait(&res_bar[ew], res_phase);
           res_phase ^= 1;
         }
-        const int nch = geglu ? NCH / 2 : NCH;  // GEGLU: the second half of the chunks are the gates
         __half* o_row = reinterpret_cast<__half*>(p.out) + out_row * p.ldo + out_col_base;
         const __half* radd_row = p.rowadd ? p.rowadd + (long)batch_idx * p.ldra + n0 : nullptr;
         const float gate = p.gate;
-        float4 pnext[4];
-        if (!complete && !geglu) {
-          const float* ws0 = p.ws + (long)f0 * (BN / CHUNK) * 128 * CHUNK;
-          const float4* src0 = reinterpret_cast<const float4*>(
-              ws0 + ((long)((half * (BN / 2)) / CHUNK) * 128 + r) * CHUNK);
+        // Chunks are processed in groups of up to GROUP: all accumulator loads of a group are issued
+        // before one wait, all results are staged before one proxy fence / warp sync, and the
+        // group's TMA stores go out together.  (Chunk-at-a-time was a ~1200-cycle serial dependency
+        // chain per 16 columns with only two warps per scheduler to hide it: tools/trace_gemm.py.)
+        constexpr int GROUP = 4;
+        constexpr int NV = geglu ? NCH / 2 : NCH;  // output chunks of this warp
 #pragma unroll
-          for (int q = 0; q < 4; ++q) pnext[q] = __ldcg(src0 + q);
-        }
+        for (int g0 = 0; g0 < NV; g0 += GROUP) {
+          uint32_t xv[GROUP][CHUNK];
+          uint32_t gv[geglu ? GROUP : 1][CHUNK];
+          bool live[GROUP];
+          const bool dbg = (sc == 0 && threadIdx.x == 128 && g0 == 0);  // group-level trace (slots 8..11)
+          if (dbg) stamp(8);
+          // ---- A: accumulator loads -----------------------------------------------------------
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          if (ch >= nch) break;
-          const int c0 = chunk_col(ch);  // accumulator column (value column in GEGLU mode)
-          const int out_c = out_col_base + c0;
-          if (out_c >= n_out_total) break;  // warp-uniform
-          const bool hi_ok = out_c + 8 < n_out_total;  // second 8-column group inside N (N % 8 == 0)
-          uint32_t v[CHUNK];
-          float x[CHUNK];
-          tmem_ld_32x32b_x16(trow + c0, v);
-          if (geglu) {
-            uint32_t g[CHUNK];
-            float gx[CHUNK];
-            tmem_ld_32x32b_x16(trow + BN / 2 + c0, g);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < CHUNK; ++j) {
-              x[j] = __uint_as_float(v[j]);
-              gx[j] = __uint_as_float(g[j]);
+          for (int i = 0; i < GROUP; ++i) {
+            const int ch = g0 + i;
+            live[i] = (ch < NV) && (out_col_base + chunk_col(ch < NV ? ch : 0) < n_out_total);
+            if (live[i]) {
+              const int c0 = chunk_col(ch);
+              tmem_ld_32x32b_x16(trow + c0, xv[i]);
+              if (geglu) tmem_ld_32x32b_x16(trow + BN / 2 + c0, gv[geglu ? i : 0]);
             }
+          }
+          tmem_ld_wait();
+          // ---- B: stream-K partials, per-column table terms, activation ---------------------------
+#pragma unroll
+          for (int i = 0; i < GROUP; ++i) {
+            if (!live[i]) continue;
+            const int c0 = chunk_col(g0 + i);
+            float x[CHUNK];
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) x[j] = __uint_as_float(xv[i][j]);
             if (!complete) {
               for (int f = f0; f <= f1; ++f) {
                 const float* wsf = p.ws + (long)f * (BN / CHUNK) * 128 * CHUNK;
                 const float4* src = reinterpret_cast<const float4*>(wsf + ((long)(c0 / CHUNK) * 128 + r) * CHUNK);
-                const float4* srcg = reinterpret_cast<const float4*>(
-                    wsf + ((long)((BN / 2 + c0) / CHUNK) * 128 + r) * CHUNK);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   const float4 t = __ldcg(src + q);
-                  const float4 u = __ldcg(srcg + q);
                   x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
-                  gx[4 * q] += u.x; gx[4 * q + 1] += u.y; gx[4 * q + 2] += u.z; gx[4 * q + 3] += u.w;
                 }
               }
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 bv = *(reinterpret_cast<const float4*>(tab_row + c0) + q);
-              const float4 bg = *(reinterpret_cast<const float4*>(tab_row + BN / 2 + c0) + q);
               x[4 * q] += bv.x; x[4 * q + 1] += bv.y; x[4 * q + 2] += bv.z; x[4 * q + 3] += bv.w;
-              gx[4 * q] += bg.x; gx[4 * q + 1] += bg.y; gx[4 * q + 2] += bg.z; gx[4 * q + 3] += bg.w;
             }
+            if (geglu) {
+              float gx[CHUNK];
 #pragma unroll
-            for (int j = 0; j < CHUNK; ++j) x[j] *= gelu_erf_f(gx[j]);
-          } else {
-            tmem_ld_wait();
+              for (int j = 0; j < CHUNK; ++j) gx[j] = __uint_as_float(gv[geglu ? i : 0][j]);
+              if (!complete) {
+                for (int f = f0; f <= f1; ++f) {
+                  const float* wsf = p.ws + (long)f * (BN / CHUNK) * 128 * CHUNK;
+                  const float4* srcg = reinterpret_cast<const float4*>(
+                      wsf + ((long)((BN / 2 + c0) / CHUNK) * 128 + r) * CHUNK);
 #pragma unroll
-            for (int j = 0; j < CHUNK; ++j) x[j] = __uint_as_float(v[j]);
-            if (!complete) {
-              // stream-K fixup: the first follower's partial of this chunk was requested one chunk
-              // earlier (pnext), the request for the next chunk goes out before this one is consumed
-              float4 pcur[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) pcur[q] = pnext[q];
-              if (ch + 1 < NCH) {
-                const float* wsn = p.ws + (long)f0 * (BN / CHUNK) * 128 * CHUNK;
-                const float4* srcn = reinterpret_cast<const float4*>(
-                    wsn + ((long)((c0 + CHUNK) / CHUNK) * 128 + r) * CHUNK);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) pnext[q] = __ldcg(srcn + q);
+                  for (int q = 0; q < 4; ++q) {
+                    const float4 u = __ldcg(srcg + q);
+                    gx[4 * q] += u.x; gx[4 * q + 1] += u.y; gx[4 * q + 2] += u.z; gx[4 * q + 3] += u.w;
+                  }
+                }
               }
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                x[4 * q] += pcur[q].x; x[4 * q + 1] += pcur[q].y; x[4 * q + 2] += pcur[q].z; x[4 * q + 3] += pcur[q].w;
+                const float4 bg = *(reinterpret_cast<const float4*>(tab_row + BN / 2 + c0) + q);
+                gx[4 * q] += bg.x; gx[4 * q + 1] += bg.y; gx[4 * q + 2] += bg.z; gx[4 * q + 3] += bg.w;
               }
-              for (int f = f0 + 1; f <= f1; ++f) {
-                const float* wsf = p.ws + (long)f * (BN / CHUNK) * 128 * CHUNK;
-                const float4* src = reinterpret_cast<const float4*>(wsf + ((long)(c0 / CHUNK) * 128 + r) * CHUNK);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float4 t = __ldcg(src + q);
-                  x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+              for (int j = 0; j < CHUNK; ++j) x[j] *= gelu_erf_f(gx[j]);
+            } else {
+              if (slow_rowadd && row_ok) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  if (q == 0 || out_col_base + c0 + 8 < n_out_total) {
+                    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(radd_row + c0) + q);
+                    const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 f = unpack_half2(ru[j]);
+                      x[8 * q + 2 * j] += f.x;
+                      x[8 * q + 2 * j + 1] += f.y;
+                    }
+                  }
                 }
               }
+              if (do_silu) {
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j) x[j] = silu_f(x[j]);
+              }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 bv = *(reinterpret_cast<const float4*>(tab_row + c0) + q);
-              x[4 * q] += bv.x; x[4 * q + 1] += bv.y; x[4 * q + 2] += bv.z; x[4 * q + 3] += bv.w;
-            }
-            if (slow_rowadd && row_ok) {
+            for (int j = 0; j < CHUNK; ++j) xv[i][j] = __float_as_uint(x[j]);
+          }
+          if (dbg) stamp(9);
+          // ---- C: residual + store --------------------------------------------------------------
+#pragma unroll
+          for (int i = 0; i < GROUP; ++i) {
+            if (!live[i]) continue;
+            const int ch = g0 + i;
+            const int c0 = chunk_col(ch);
+            const int out_c = out_col_base + c0;
+            const bool hi_ok = out_c + 8 < n_out_total;  // second 8-column group inside N (N % 8 == 0)
+            if (nchw) {
+              if (row_ok) {
+                float* o = reinterpret_cast<float*>(p.out);
+                const long hw = p.conv ? (long)p.H * p.W : (long)p.rows_per_batch;
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j) {
+                  const int col = out_c + j;
+                  if (col < n_out_total) o[((long)batch_idx * n_out_total + col) * hw + pix] = __uint_as_float(xv[i][j]);
+                }
+              }
+            } else if (TMA_EPI) {
+              // box `ch`: row `lane` is 32 B; SWIZZLE_32B puts 16-byte chunk q at (q ^ ((lane >> 2) & 1)).
+              // The residual (if any) was landed here by TMA; the result replaces it in place.  Rows /
+              // columns outside the tensor are clipped by the TMA store.
+              uint8_t* box = wstage + ch * C::BOX_BYTES + lane * 32;
+              const int swz = (lane >> 2) & 1;
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
-                if (q == 0 || hi_ok) {
-                  const uint4 rv = __ldg(reinterpret_cast<const uint4*>(radd_row + c0) + q);
+                uint4* slot = reinterpret_cast<uint4*>(box + ((q ^ swz) << 4));
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(xv[i][8 * q + j]);
+                if (has_res) {
+                  const uint4 rv = *slot;
                   const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
                     const float2 f = unpack_half2(ru[j]);
-                    x[8 * q + 2 * j] += f.x;
-                    x[8 * q + 2 * j + 1] += f.y;
+                    y[2 * j] = fmaf(gate, y[2 * j], f.x);
+                    y[2 * j + 1] = fmaf(gate, y[2 * j + 1], f.y);
                   }
                 }
+                *slot = make_uint4(pack_half2(y[0], y[1]), pack_half2(y[2], y[3]), pack_half2(y[4], y[5]),
+                                   pack_half2(y[6], y[7]));
               }
-            }
-            if (do_silu) {
-#pragma unroll
-              for (int j = 0; j < CHUNK; ++j) x[j] = silu_f(x[j]);
-            }
-          }
-          if (row_ok) {
-            if (nchw) {
-              float* o = reinterpret_cast<float*>(p.out);
-              const long hw = p.conv ? (long)p.H * p.W : (long)p.rows_per_batch;
-#pragma unroll
-              for (int j = 0; j < CHUNK; ++j) {
-                const int col = out_c + j;
-                if (col < n_out_total) o[((long)batch_idx * n_out_total + col) * hw + pix] = x[j];
-              }
-            } else if (TMA_EPI) {
-              // unreachable: TMA_EPI handles the store below (outside the row_ok guard)
-            } else {
+            } else if (row_ok) {
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
                 if (q == 0 || hi_ok) {
                   float y[8];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) y[j] = x[8 * q + j];
+                  for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(xv[i][8 * q + j]);
                   if (has_res) {
                     const uint4 rv = resv[TMA_EPI ? 0 : ch][q];
                     const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
@@ -592,52 +612,29 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                       y[2 * j + 1] = fmaf(gate, y[2 * j + 1], f.y);
                     }
                   }
-                  uint4 ov;
-                  ov.x = pack_half2(y[0], y[1]);
-                  ov.y = pack_half2(y[2], y[3]);
-                  ov.z = pack_half2(y[4], y[5]);
-                  ov.w = pack_half2(y[6], y[7]);
-                  *(reinterpret_cast<uint4*>(o_row + c0) + q) = ov;
+                  *(reinterpret_cast<uint4*>(o_row + c0) + q) =
+                      make_uint4(pack_half2(y[0], y[1]), pack_half2(y[2], y[3]), pack_half2(y[4], y[5]),
+                                 pack_half2(y[6], y[7]));
                 }
               }
             }
           }
+          if (dbg) stamp(10);
           if (TMA_EPI && !nchw) {
-            // box `ch`: row `lane` is 32 B; SWIZZLE_32B puts 16-byte chunk q at (q ^ ((lane >> 2) & 1)).
-            // The residual (if any) was landed here by TMA; the result replaces it in place and one
-            // elected lane sends the box out.  Rows / columns outside the tensor are clipped by TMA.
-            uint8_t* box = wstage + ch * C::BOX_BYTES + lane * 32;
-            const int swz = (lane >> 2) & 1;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              uint4* slot = reinterpret_cast<uint4*>(box + ((q ^ swz) << 4));
-              float y[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) y[j] = x[8 * q + j];
-              if (has_res) {
-                const uint4 rv = *slot;
-                const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = unpack_half2(ru[j]);
-                  y[2 * j] = fmaf(gate, y[2 * j], f.x);
-                  y[2 * j + 1] = fmaf(gate, y[2 * j + 1], f.y);
-                }
-              }
-              uint4 ov;
-              ov.x = pack_half2(y[0], y[1]);
-              ov.y = pack_half2(y[2], y[3]);
-              ov.z = pack_half2(y[4], y[5]);
-              ov.w = pack_half2(y[6], y[7]);
-              *slot = ov;
-            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              if (p.conv) tma_store_4d(&tmO, wstage + ch * C::BOX_BYTES, out_c, tc1, tc2, tc3);
-              else tma_store_2d(&tmO, wstage + ch * C::BOX_BYTES, out_c, tc1);
+#pragma unroll
+              for (int i = 0; i < GROUP; ++i) {
+                if (!live[i]) continue;
+                const int ch = g0 + i;
+                const int out_c = out_col_base + chunk_col(ch);
+                if (p.conv) tma_store_4d(&tmO, wstage + ch * C::BOX_BYTES, out_c, tc1, tc2, tc3);
+                else tma_store_2d(&tmO, wstage + ch * C::BOX_BYTES, out_c, tc1);
+              }
             }
           }
+          if (dbg) stamp(11);
         }
         if (TMA_EPI && lane == 0) tma_store_commit();
         if (sc == 0 && threadIdx.x == 128) stamp(5);

@@ -1,4 +1,5 @@
-"""Per-CTA phase timeline of one GEMM launch (idiff_set_gemm_trace).  Usage: trace_gemm.py <shape>"""
+"""Per-CTA phase timeline of one GEMM launch (idiff_set_gemm_trace: 16 %globaltimer stamps per CTA).
+Usage: python tools/trace_gemm.py <shape> [...]"""
 import os
 import sys
 
@@ -18,8 +19,11 @@ shapes = {
     "conv1280": lambda: (r(B * 256, 1280), r(1280, 11520, sc=0.01), dict(conv=(B, 16, 16, 1280), residual=r(B * 256, 1280))),
     "conv320": lambda: (r(B * 4096, 320), r(320, 2880, sc=0.02), dict(conv=(B, 64, 64, 320), residual=r(B * 4096, 320))),
 }
+names = ["entry", "1st tile", "seg0 issued", "acc0 ready", "fixup done", "epi0 done", "loops done", "exit",
+         "c0 start", "c0 computed", "c0 staged", "c0 store issued", "c1 start", "c1 computed", "c1 staged",
+         "c1 store issued"]
 lib = _lib.load()
-trace = torch.zeros(256 * 8, dtype=torch.int64, device=dev)
+trace = torch.zeros(256 * 16, dtype=torch.int64, device=dev)
 for name in sys.argv[1:]:
     a, w, kw = shapes[name]()
     bias = torch.randn(w.shape[0], device=dev)
@@ -31,13 +35,12 @@ for name in sys.argv[1:]:
     ops.gemm(a, w, bias, **kw)
     torch.cuda.synchronize()
     lib.idiff_set_gemm_trace(None)
-    t = trace.view(256, 8).cpu()
+    t = trace.view(256, 16).cpu()
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
     rel = (t - t0).float() / 1e3  # us
-    names = ["entry", "1st tile", "seg0 issued", "acc0 ready", "fixup done", "epi0 done", "loops done", "exit"]
     print(f"== {name}: {t.shape[0]} CTAs, kernel span {rel[:, 7].max():.1f} us")
     for i, n in enumerate(names):
         col = rel[:, i][t[:, i] > 0]
         if col.numel():
-            print(f"   {n:12s} min {col.min():7.2f}  median {col.median():7.2f}  max {col.max():7.2f} us")
+            print(f"   {n:16s} min {col.min():7.2f}  median {col.median():7.2f}  max {col.max():7.2f} us")
