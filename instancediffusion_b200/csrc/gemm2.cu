@@ -190,7 +190,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       p.trace[(long)cta * 16 + slot] = t;
     }
   };
-  if (threadIdx.x == 0) stamp(0);
+  if (threadIdx.x == 0) {
+    stamp(0);
+    if (p.trace) p.trace[(long)cta * 16 + 12] = (unsigned long long)clock64();  // SM clock at entry
+  }
 
   auto tile_origin = [&](int tile, int& n0, int& m0, int& b0, int& h0, int& w0) {
     const int n_tile = tile % p.n_tiles;
@@ -480,6 +483,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
           tmem_ld_wait();
+          if (dbg) stamp(14);
           // ---- B: stream-K partials, per-column table terms, activation ---------------------------
 #pragma unroll
           for (int i = 0; i < GROUP; ++i) {
@@ -654,7 +658,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (TMA_EPI && warp >= 4 && lane == 0) tma_store_wait_read();  // boxes must outlive their stores
   if (threadIdx.x == 128) stamp(6);
   __syncthreads();
-  if (threadIdx.x == 0) stamp(7);
+  if (threadIdx.x == 0) {
+    stamp(7);
+    if (p.trace) p.trace[(long)cta * 16 + 13] = (unsigned long long)clock64();  // SM clock at exit
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<C::TMEM_COLS>(tmem_base);

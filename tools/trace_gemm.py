@@ -31,6 +31,8 @@ for name in sys.argv[1:]:
         ops.gemm(a, w, bias, **kw)
     torch.cuda.synchronize()
     trace.zero_()
+    for _ in range(200):  # keep the GPU busy so the traced launch runs at load clocks
+        ops.gemm(a, w, bias, **kw)
     lib.idiff_set_gemm_trace(trace.data_ptr())
     ops.gemm(a, w, bias, **kw)
     torch.cuda.synchronize()
@@ -39,8 +41,10 @@ for name in sys.argv[1:]:
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
     rel = (t - t0).float() / 1e3  # us
-    print(f"== {name}: {t.shape[0]} CTAs, kernel span {rel[:, 7].max():.1f} us")
-    for i, n in enumerate(names):
+    mhz = ((t[:, 13] - t[:, 12]).float() / (t[:, 7] - t[:, 0]).float().clamp(min=1) * 1e3).median()
+    print(f"== {name}: {t.shape[0]} CTAs, kernel span {rel[:, 7].max():.1f} us, SM clock during kernel ~{mhz:.0f} MHz")
+    names[14] = "c0 tmem loaded"
+    for i, n in list(enumerate(names[:12])) + [(14, names[14])]:
         col = rel[:, i][t[:, i] > 0]
         if col.numel():
             print(f"   {n:16s} min {col.min():7.2f}  median {col.median():7.2f}  max {col.max():7.2f} us")
