@@ -458,6 +458,124 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __half* o_row = reinterpret_cast<__half*>(p.out) + out_row * p.ldo + out_col_base;
         const __half* radd_row = p.rowadd ? p.rowadd + (long)batch_idx * p.ldra + n0 : nullptr;
         const float gate = p.gate;
+        if (TMA_EPI && !nchw) {
+          // Compact rolled loop (one 16-column chunk per trip, ~150 instructions, explicit
+          // ld/st.shared): the unrolled variant below was instruction-fetch bound for short-K layers
+          // (26 % stall_no_inst, generic LD for shared operands; profiles/).
+          constexpr int NVT = geglu ? NCH / 2 : NCH;
+          const int cbase = geglu ? half * (BN / 4) : half * (BN / 2);
+          const uint32_t tab_s = smem_u32(tab_row);
+          const uint32_t box_s = smem_u32(wstage) + lane * 32;
+          const uint32_t sw16 = ((lane >> 2) & 1) << 4;
+          auto lds4 = [](uint32_t a, float (&f)[4]) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                         : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(a));
+          };
+#pragma unroll 1
+          for (int ch = 0; ch < NVT; ++ch) {
+            const int c0 = cbase + ch * CHUNK;
+            const int out_c = out_col_base + c0;
+            if (out_c >= n_out_total) break;  // warp-uniform
+            uint32_t v[CHUNK];
+            float x[CHUNK];
+            tmem_ld_32x32b_x16(trow + c0, v);
+            if (geglu) {
+              uint32_t g[CHUNK];
+              float gx[CHUNK];
+              tmem_ld_32x32b_x16(trow + BN / 2 + c0, g);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < CHUNK; ++j) {
+                x[j] = __uint_as_float(v[j]);
+                gx[j] = __uint_as_float(g[j]);
+              }
+              if (!complete) {
+                for (int f = f0; f <= f1; ++f) {
+                  const float* wsf = p.ws + (long)f * (BN / CHUNK) * 128 * CHUNK;
+                  const float4* src = reinterpret_cast<const float4*>(wsf + ((long)(c0 / CHUNK) * 128 + r) * CHUNK);
+                  const float4* srcg = reinterpret_cast<const float4*>(
+                      wsf + ((long)((BN / 2 + c0) / CHUNK) * 128 + r) * CHUNK);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float4 t = __ldcg(src + q);
+                    const float4 u = __ldcg(srcg + q);
+                    x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+                    gx[4 * q] += u.x; gx[4 * q + 1] += u.y; gx[4 * q + 2] += u.z; gx[4 * q + 3] += u.w;
+                  }
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float bv[4], bg[4];
+                lds4(tab_s + (c0 + 4 * q) * 4, bv);
+                lds4(tab_s + (BN / 2 + c0 + 4 * q) * 4, bg);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[4 * q + j] = (x[4 * q + j] + bv[j]) * gelu_erf_f(gx[4 * q + j] + bg[j]);
+              }
+            } else {
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < CHUNK; ++j) x[j] = __uint_as_float(v[j]);
+              if (!complete) {
+                for (int f = f0; f <= f1; ++f) {
+                  const float* wsf = p.ws + (long)f * (BN / CHUNK) * 128 * CHUNK;
+                  const float4* src = reinterpret_cast<const float4*>(wsf + ((long)(c0 / CHUNK) * 128 + r) * CHUNK);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float4 t = __ldcg(src + q);
+                    x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+                  }
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float bv[4];
+                lds4(tab_s + (c0 + 4 * q) * 4, bv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[4 * q + j] += bv[j];
+              }
+              if (slow_rowadd && row_ok) {
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j)
+                  if (out_c + j < n_out_total) x[j] += __half2float(radd_row[c0 + j]);
+              }
+              if (do_silu) {
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j) x[j] = silu_f(x[j]);
+              }
+            }
+            // box `ch`: row `lane` is 32 B; SWIZZLE_32B puts 16-byte chunk q at (q ^ ((lane >> 2) & 1)).
+            // The residual (if any) was landed here by TMA; the result replaces it in place.
+            const uint32_t boxa = box_s + ch * C::BOX_BYTES;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const uint32_t slot = boxa + ((q << 4) ^ sw16);
+              float y[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y[j] = x[8 * q + j];
+              if (has_res) {
+                uint32_t ru[4];
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+                             : "=r"(ru[0]), "=r"(ru[1]), "=r"(ru[2]), "=r"(ru[3]) : "r"(slot));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = unpack_half2(ru[j]);
+                  y[2 * j] = fmaf(gate, y[2 * j], f.x);
+                  y[2 * j + 1] = fmaf(gate, y[2 * j + 1], f.y);
+                }
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(slot), "r"(pack_half2(y[0], y[1])),
+                           "r"(pack_half2(y[2], y[3])), "r"(pack_half2(y[4], y[5])), "r"(pack_half2(y[6], y[7]))
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.conv) tma_store_4d(&tmO, wstage + ch * C::BOX_BYTES, out_c, tc1, tc2, tc3);
+              else tma_store_2d(&tmO, wstage + ch * C::BOX_BYTES, out_c, tc1);
+            }
+          }
+        } else {
         // Chunks are processed in groups of up to GROUP: all accumulator loads of a group are issued
         // before one wait, all results are staged before one proxy fence / warp sync, and the
         // group's TMA stores go out together.  (Chunk-at-a-time was a ~1200-cycle serial dependency
@@ -640,6 +758,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           if (dbg) stamp(11);
         }
+        }  // direct / grouped epilogue
         if (TMA_EPI && lane == 0) tma_store_commit();
         if (sc == 0 && threadIdx.x == 128) stamp(5);
         tc_fence_before();
