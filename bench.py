@@ -294,20 +294,42 @@ def roofline_pass(model, device, peaks):
     breakdown = {k: {"share": a[0] / tot, "launches": a[3] // 3, "ms": a[0] / 3 * 1e3,
                      "tflops": (a[1] / a[0] / 1e12) if a[1] else None,
                      "gbs": a[2] / a[0] / 1e9} for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])}
-    dom = max(agg.items(), key=lambda kv: kv[1][0])
+    # kernel classes: every linear / conv3x3 / GEGLU launch is the same kernel template
+    # (csrc/gemm2.cu gemm2_kernel<BN, MODE, TMA_EPI>), so they compete as one class for "dominant"
+    fam = {"gemm2_kernel": [0.0, 0.0, 0.0, 0]}
+    for k, a in agg.items():
+        tgt = "gemm2_kernel" if k in ("gemm", "conv3x3", "gemm_geglu") else k
+        f = fam.setdefault(tgt, [0.0, 0.0, 0.0, 0])
+        for i in range(4):
+            f[i] += a[i]
+    traffic_tab = {}
+    try:
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+    except Exception:
+        pass
+    dom = max(fam.items(), key=lambda kv: kv[1][0])
     kind, a = dom
+    traffic = traffic_tab.get(kind, {}).get("dram_bytes_per_launch")
     if a[1] > 0:
         achieved = a[1] / a[0] / 1e12
         peak = peaks.get("bf16_tflops_sustained") or 1400.0
         roof = {"bound": "tensor", "kernel": kind, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic, "launches_per_forward": a[3] // 3,
+                "share_of_forward": a[0] / tot,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"}
     else:
         achieved = a[2] / a[0] / 1e9
         peak = peaks.get("hbm_gbs") or 6650.0
         roof = {"bound": "hbm", "kernel": kind, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"}
+    # the north-star kernel (fused gated self-attention at the 64x64 level) reported next to it
+    att = agg.get("attention_d40")
+    if att and att[0] > 0:
+        peak = peaks.get("bf16_tflops_sustained") or 1400.0
+        roof["attention_d40"] = {"achieved": att[1] / att[0] / 1e12, "unit": "TFLOP/s", "frac": att[1] / att[0] / 1e12 / peak,
+                                 "share_of_forward": att[0] / tot,
+                                 "traffic": traffic_tab.get("attention2_kernel", {}).get("dram_bytes_per_launch")}
     n_launch = sum(a[3] for a in agg.values()) // 3
     return roof, breakdown, n_launch
 
@@ -444,4 +466,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        import torch.distributed as _dist
+        if _dist.is_available() and _dist.is_initialized():
+            _dist.destroy_process_group()

@@ -14,9 +14,15 @@
 //     no padded columns, half the A-tile traffic of 128-wide tiles.
 //   * two TMEM accumulator buffers: the epilogue of segment i overlaps the MMAs of segment i+1;
 //     8 epilogue warps (2 per TMEM lane quarter) so short-K layers are not epilogue-bound.
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + UMMA issuer,
-// warps 2..9 epilogue.  conv3x3 gathers the A tile tap by tap with a 4-D TMA box (zero fill at
-// the borders), exactly as in gemm.cu.
+//   * epilogue (measured with the built-in per-CTA phase trace, tools/trace_gemm.py): per-tile
+//     bias / time-embedding terms come from a shared-memory table; short-K layers move the residual
+//     in and the result out as TMA boxes through a swizzled staging buffer (compact rolled loop);
+//     long-K convolutions keep the deep operand ring and prefetch their residual rows into
+//     registers before the accumulator is ready.  One kernel per (BN, epilogue mode, TMA epilogue).
+// Warp roles (384 threads = 3 warpgroups): warp 0 TMA producer, warp 1 TMEM allocator + UMMA
+// issuer (warps 2-3 idle; the group gives registers back with setmaxnreg), warps 4..11 epilogue.
+// conv3x3 gathers the A tile tap by tap with a 4-D TMA box (zero fill at the borders), exactly as
+// in gemm.cu.
 #include "../../include/idiff_b200.h"
 #include "common.cuh"
 #include "host.cuh"
