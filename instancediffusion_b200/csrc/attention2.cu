@@ -1,22 +1,26 @@
-// Attention v2 for sm_100a (head_dim 40, the 64x64-resolution level that carries 83 % of the
-// attention time): two 128-query tiles per CTA processed in ping-pong.
+// Attention v2 for sm_100a (head_dim 40: the 64x64-resolution level that carries 83 % of the
+// attention time).  Two 128-query tiles per CTA, 64-key blocks, TWO CTAs PER SM.
 //
-// What changed against attention.cu, and why (measured: profiles/r1_v0_*):
-//   * 2 Q tiles / 8 softmax warps per CTA: the K/V tiles are fetched once for 256 queries and each
-//     SM sub-partition has two softmax warps to hide latency; S_q(j+1) = Q_q K(j+1)^T is issued as
-//     soon as softmax_q(j) has pulled S_q(j) into registers, so the tensor pipe works while the
-//     exponentials run.
-//   * single pass over S: all 128 scores of a row are read from TMEM once into registers.
-//   * exp2 on packed halves (ex2.approx.ftz.f16x2): half the MUFU work, and the result is already
-//     the fp16 pair the P.V product wants.  d=40 attention is exp-bound.
-//   * the row sums l = sum_k P are computed by the tensor core as P . 1 (a 16-column block of
-//     ones in shared memory, UMMA N=16) -- exactly the rounded P that multiplies V.
+// Why it looks like this (measurements: tools/micro/umma_bench.cu, IDIFF_ATT2_TRACE timelines,
+// profiles/README.md):
+//   * d=40 attention is bounded by the MUFU pipe (16 ex2/clk/SM = 2048 clk per 128 keys of a 256-query
+//     CTA), but what the first versions actually spent was hand-off latency: every mbarrier wait /
+//     arrive, fence.proxy.async, tcgen05.wait::ld and tcgen05.commit round trip costs 100-350 clk,
+//     one tcgen05.mma costs >= 45 clk whatever its N, and with two softmax warps per scheduler there
+//     is nothing to issue meanwhile.  A traced 64-key step took ~3300 clk of which ~1700 were the 64
+//     exponentials; removing the exponentials, the P.V products or the loads each changed nothing.
+//   * So the kernel is sized to run two CTAs per SM (<= 113 KB shared memory, 256 TMEM columns,
+//     <= 104 registers in the softmax warps): four softmax warps per scheduler from two independent
+//     CTAs cover each other's hand-offs, two UMMA issuer threads share the tensor pipe, and one CTA's
+//     prologue / epilogue overlaps the other's main loop.
+//   * Row sums are accumulated in registers (fp32) instead of a second UMMA per k-step against a
+//     block of ones: that halves the UMMA count.
 //   * lazy rescaling: the running maximum used for the exponent is only advanced when it grew by
-//     more than 2^8 in the exp2 domain, so the O/L rescale in TMEM is rare (P <= 256 fits fp16).
+//     more than 2^8 in the exp2 domain, so the O rescale in TMEM is rare (P <= 256 fits fp16).
+//   * the UMMA issuer is event-driven: each Q tile advances on its own barriers.
 // Warp roles (384 threads = 3 warpgroups): warp 0 TMA producer, warp 1 TMEM allocator + UMMA issuer
 // (warps 2-3 idle; the group releases registers with setmaxnreg.dec), warps 4..7 softmax of Q tile 0,
-// warps 8..11 softmax of Q tile 1 (one thread per query row, 232 registers via setmaxnreg.inc: a
-// row's 128 scores and its 64 packed probabilities live in registers).
+// warps 8..11 softmax of Q tile 1 (one thread per query row).
 #include "../../include/idiff_b200.h"
 #include "common.cuh"
 #include "host.cuh"
@@ -26,7 +30,7 @@ namespace att2 {
 
 constexpr int THREADS = 384;  // 3 warpgroups: {TMA, UMMA, 2 idle} + softmax(Q0) + softmax(Q1)
 constexpr int BQ = 128;
-constexpr int BKV = 128;
+constexpr int BKV = 64;
 
 struct Params {
   int heads, nq, n0, n1, kv1_broadcast;
@@ -41,14 +45,17 @@ struct Cfg {
   static constexpr int KSTEPS = (D + 15) / 16;
   static constexpr int DV = 64;
   static constexpr int STAGES = 3;
-  static constexpr int Q_BYTES = BQ * 128;         // per Q tile
-  static constexpr int KV_BYTES = BKV * 128;       // one of K or V
-  static constexpr int P_BYTES = 2 * BQ * 128;     // per Q tile: two 64-key chunks
-  static constexpr int ONES_BYTES = 4096;          // [2 chunks][16 rows][128 B] of fp16 1.0
-  static constexpr int SMEM_BYTES = 2 * Q_BYTES + STAGES * 2 * KV_BYTES + 2 * P_BYTES + ONES_BYTES + 1024 + 256;
-  // TMEM columns
-  static constexpr int S_COL0 = 0, S_COL1 = 128;
-  static constexpr int O_COL0 = 256, L_COL0 = 320, O_COL1 = 336, L_COL1 = 400;
+  static constexpr int Q_BYTES = BQ * 128;     // per Q tile
+  static constexpr int KV_BYTES = BKV * 128;   // one of K or V: 64 keys x 128 B (64 halves, d <= 64)
+  static constexpr int P_BYTES = BQ * 128;     // P of one tile: 128 rows x 64 keys
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int TRACE_BYTES = 2048;     // TRACE instantiation only
+  // 2 x (this + 1 KiB the system reserves per CTA) must fit the SM's 228 KiB: no alignment slack, the
+  // kernel checks that the dynamic shared memory window starts 1024-byte aligned.
+  static constexpr int SMEM_BYTES = 2 * Q_BYTES + STAGES * 2 * KV_BYTES + 2 * P_BYTES + BAR_BYTES;
+  // TMEM columns (256 allocated): S[tile] 64 each, then O[tile] 64 each
+  static constexpr int S_COL = 0, O_COL = 128;
+  static constexpr int TMEM_COLS = 256;
 };
 
 IDIFF_DEVICE void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -70,38 +77,64 @@ IDIFF_DEVICE void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
       : "memory");
 }
 
-IDIFF_DEVICE uint32_t exp2_pack_h2(float x0, float x1) {
-  // {2^x0, 2^x1} as packed fp16.  ex2.approx.f16x2 was measured here first: on sm_100 it lowers to
-  // two scalar MUFU.EX2.F16 + a PRMT and ran at about half the fp32 MUFU rate (profiles/), so the
-  // exponentials stay fp32 MUFU.EX2 followed by one F2FP pack.
-  return pack_half2(exp2_approx(x0), exp2_approx(x1));
+// tcgen05.wait::ld that names the registers of the load it completes, so the compiler cannot move a
+// consumer of those registers above the wait (the load of block j+1 is in flight during block j).
+IDIFF_DEVICE void tmem_ld_wait_dep(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                 "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]),
+                 "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]),
+                 "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]),
+                 "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+IDIFF_DEVICE void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
 }
 
-template <int D>
-__global__ void __launch_bounds__(THREADS, 1)
+// ptxas schedules within basic blocks and, left alone, hoists every MUFU of a block above the TMEM
+// traffic that should overlap with it (the PTX order is not kept).  A never-taken, data-dependent
+// branch ends the basic block and pins the order of the pieces on either side.  0xffffffff is not a
+// value F2FP can produce (NaN packs as 0x7fff), so the trap is unreachable.
+IDIFF_DEVICE void sched_fence(uint32_t packed) {
+  if (packed == 0xffffffffu) asm volatile("trap;\n");
+}
+
+// TRACE (IDIFF_ATT2_TRACE=1): one CTA records clock stamps of blocks 16..23 in shared memory and prints
+// them at exit -- a timeline of the hand-offs that costs the measured kernel nothing but a few STS.
+template <int D, bool TRACE = false>
+__global__ void __launch_bounds__(THREADS, 2)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                   const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                   const __grid_constant__ CUtensorMap tmV1, const Params p) {
   using C = Cfg<D>;
   constexpr int STAGES = C::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {  // SWIZZLE_128B tiles need it; no slack is budgeted (see Cfg)
+    if (threadIdx.x == 0) printf("idiff: attention2 shared memory window not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* sQ = smem;                                  // [2][16 KiB]
-  uint8_t* sK = sQ + 2 * C::Q_BYTES;                   // [STAGES][16 KiB]
-  uint8_t* sV = sK + STAGES * C::KV_BYTES;             // [STAGES][16 KiB]
-  uint8_t* sP = sV + STAGES * C::KV_BYTES;             // [2][32 KiB]
-  uint8_t* sOnes = sP + 2 * C::P_BYTES;                // 4 KiB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + C::ONES_BYTES);
+  uint8_t* sK = sQ + 2 * C::Q_BYTES;                   // [STAGES][8 KiB]
+  uint8_t* sV = sK + STAGES * C::KV_BYTES;             // [STAGES][8 KiB]
+  uint8_t* sP = sV + STAGES * C::KV_BYTES;             // [tile][16 KiB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * C::P_BYTES);
   uint64_t* q_full = bars;               // 1
   uint64_t* k_full = bars + 1;           // STAGES
   uint64_t* v_full = k_full + STAGES;    // STAGES
   uint64_t* kv_empty = v_full + STAGES;  // STAGES
-  uint64_t* s_full = kv_empty + STAGES;  // 2
-  uint64_t* s_free = s_full + 2;         // 2 (128 arrivals)
-  uint64_t* p_full = s_free + 2;         // 2 (128 arrivals)
-  uint64_t* pv_done = p_full + 2;        // 2
+  uint64_t* s_full = kv_empty + STAGES;  // [tile]
+  uint64_t* s_free = s_full + 2;         // [tile] (128 arrivals)
+  uint64_t* p_full = s_free + 2;         // [tile] (128 arrivals)
+  uint64_t* pv_done = p_full + 2;        // [tile]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint32_t* trace_buf = reinterpret_cast<uint32_t*>(sP + 2 * C::P_BYTES + C::BAR_BYTES);  // TRACE only
+  const bool traced = TRACE && blockIdx.x == 3 && blockIdx.y == 2 && blockIdx.z == 0;
+  auto stamp = [&](int slot) {
+    if (TRACE && traced) trace_buf[slot] = clock();
+  };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -122,19 +155,15 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_init(&v_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    for (int q = 0; q < 2; ++q) {
-      mbar_init(&s_full[q], 1);
-      mbar_init(&s_free[q], 128);
-      mbar_init(&p_full[q], 128);
-      mbar_init(&pv_done[q], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&pv_done[i], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
-  // the block of ones that turns the row sums into a UMMA (every element is 1.0, so any layout works)
-  for (int i = threadIdx.x; i < C::ONES_BYTES / 4; i += THREADS)
-    reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3C003C00u;
-  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -143,7 +172,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   // Register re-partition between warpgroups (the setmaxnreg must sit at the head of each role
   // branch so that ptxas allocates the branch bodies against the new limits).
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -167,17 +196,14 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_f16(BQ, BKV, 0, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(BQ, C::DV, 0, 0, /*B MN-major*/ 1);
-      constexpr uint32_t idesc_l = make_idesc_f16(BQ, 16, 0, 0, 0);
       // Every descriptor here shares its high word (SBO = 1024 B, version 1, SWIZZLE_128B); the low
       // word is (address >> 4) | (LBO >> 4) << 16, so stepping an operand by X bytes is lo += X >> 4.
-      // The issuing thread therefore spends one integer add per UMMA (the tiles are small: N = 64 /
-      // 16 UMMAs last 32 / 8 clocks, so descriptor arithmetic in the issue loop would dominate).
+      // The issuing thread therefore spends one integer add per UMMA.
       constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
       constexpr uint32_t LBO_K = (16u >> 4) << 16;             // K-major operands (unused field)
-      constexpr uint32_t LBO_V = ((BKV * 128u) >> 4) << 16;    // MN-major V: next 64-wide d chunk
+      constexpr uint32_t LBO_V = ((BKV * 128u) >> 4) << 16;    // MN-major V: next 64-wide d chunk (unused)
       const uint32_t q_lo0 = (smem_u32(sQ) >> 4) | LBO_K;
       const uint32_t p_lo0 = (smem_u32(sP) >> 4) | LBO_K;
-      const uint32_t ones_lo = (smem_u32(sOnes) >> 4) | LBO_K;
       const uint32_t k_lo0 = (smem_u32(sK) >> 4) | LBO_K;
       const uint32_t v_lo0 = (smem_u32(sV) >> 4) | LBO_V;
       auto umma_lo = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
@@ -190,144 +216,180 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(acc)
             : "memory");
       };
-      auto issue_qk = [&](int q, int j) {
+      auto issue_qk = [&](int q, int n) {  // S[q] = Q_q . K(n)^T
         const uint32_t q_lo = q_lo0 + q * (C::Q_BYTES >> 4);
-        const uint32_t k_lo = k_lo0 + (j % STAGES) * (C::KV_BYTES >> 4);
-        const uint32_t d_tmem = tmem_base + (q ? C::S_COL1 : C::S_COL0);
+        const uint32_t k_lo = k_lo0 + (n % STAGES) * (C::KV_BYTES >> 4);
+        const uint32_t d_tmem = tmem_base + C::S_COL + q * 64;
 #pragma unroll
         for (int kk = 0; kk < C::KSTEPS; ++kk)
           umma_lo(d_tmem, q_lo + kk * 2, k_lo + kk * 2, idesc_qk, kk > 0 ? 1u : 0u);
         umma_commit(&s_full[q]);
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      for (int j = 0; j < T; ++j) {
-        const int st = j % STAGES;
-        if (j + 1 < T) {
-          mbar_wait(&k_full[(j + 1) % STAGES], ((j + 1) / STAGES) & 1);
-          for (int q = 0; q < 2; ++q) {
-            mbar_wait(&s_free[q], j & 1);  // softmax_q(j) holds S_q(j) in registers
-            tc_fence_after();
-            issue_qk(q, j + 1);
-          }
-        }
-        mbar_wait(&v_full[st], (j / STAGES) & 1);
-        const uint32_t v_lo = v_lo0 + st * (C::KV_BYTES >> 4);
-        for (int q = 0; q < 2; ++q) {
-          mbar_wait(&p_full[q], j & 1);
-          tc_fence_after();
-          const uint32_t p_lo = p_lo0 + q * (C::P_BYTES >> 4);
-          const uint32_t o_tmem = tmem_base + (q ? C::O_COL1 : C::O_COL0);
-          const uint32_t l_tmem = tmem_base + (q ? C::L_COL1 : C::L_COL0);
-          const uint32_t acc0 = j > 0 ? 1u : 0u;
+      auto issue_pv = [&](int q, int n) {  // O[q] += P[q] . V(n)
+        const uint32_t v_lo = v_lo0 + (n % STAGES) * (C::KV_BYTES >> 4);
+        const uint32_t p_lo = p_lo0 + q * (C::P_BYTES >> 4);
+        const uint32_t o_tmem = tmem_base + C::O_COL + q * 64;
+        const uint32_t acc0 = n > 0 ? 1u : 0u;
 #pragma unroll
-          for (int kk = 0; kk < BKV / 16; ++kk) {
-            const uint32_t a_lo = p_lo + (kk >> 2) * ((BQ * 128) >> 4) + (kk & 3) * 2;
-            umma_lo(o_tmem, a_lo, v_lo + kk * (2048 >> 4), idesc_pv, kk > 0 ? 1u : acc0);
-            umma_lo(l_tmem, a_lo, ones_lo + (kk >> 2) * (2048 >> 4) + (kk & 3) * 2, idesc_l, kk > 0 ? 1u : acc0);
+        for (int kk = 0; kk < BKV / 16; ++kk)
+          umma_lo(o_tmem, p_lo + kk * 2, v_lo + kk * (2048 >> 4), idesc_pv, kk > 0 ? 1u : acc0);
+        umma_commit(&pv_done[q]);
+      };
+      // Event-driven issue: each Q tile advances on its own barriers (S pulled into registers -> next
+      // Q.K^T, P written -> P.V).  Per tile the block indices only grow, and every test asks for the
+      // completion right after one this thread has already observed, so parities are unambiguous.
+      mbar_wait(q_full, 0);
+      int qk_n[2] = {0, 0}, pv_n[2] = {0, 0};
+      long long t_idle = 0;
+      while (pv_n[0] < T || pv_n[1] < T) {
+        bool progress = false;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int nq = qk_n[q];
+          if (nq < T && (nq == 0 || mbar_test(&s_free[q], (nq - 1) & 1)) &&
+              mbar_test(&k_full[nq % STAGES], (nq / STAGES) & 1)) {
+            tc_fence_after();
+            if (nq >= 16 && nq < 24) stamp(128 + (q * 8 + nq - 16) * 4 + 0);
+            issue_qk(q, nq);
+            if (nq >= 16 && nq < 24) stamp(128 + (q * 8 + nq - 16) * 4 + 1);
+            qk_n[q] = nq + 1;
+            progress = true;
           }
-          umma_commit(&pv_done[q]);
+          const int np = pv_n[q];
+          if (np < qk_n[q] && mbar_test(&p_full[q], np & 1) &&
+              mbar_test(&v_full[np % STAGES], (np / STAGES) & 1)) {
+            tc_fence_after();
+            if (np >= 16 && np < 24) stamp(128 + (q * 8 + np - 16) * 4 + 2);
+            issue_pv(q, np);
+            if (np >= 16 && np < 24) stamp(128 + (q * 8 + np - 16) * 4 + 3);
+            pv_n[q] = np + 1;
+            if (pv_n[q ^ 1] > np) umma_commit(&kv_empty[np % STAGES]);  // both tiles are past block np
+            progress = true;
+          }
         }
-        umma_commit(&kv_empty[st]);
+        if (progress) {
+          t_idle = 0;
+        } else {  // bounded like mbar_wait: a protocol bug traps instead of hanging the GPU
+          if (t_idle == 0) t_idle = clock64();
+          else if (clock64() - t_idle > 8000000000LL) {
+            printf("idiff: attention2 issue loop stalled block=(%d,%d,%d) qk=(%d,%d) pv=(%d,%d)\n", blockIdx.x,
+                   blockIdx.y, blockIdx.z, qk_n[0], qk_n[1], pv_n[0], pv_n[1]);
+            __trap();
+          }
+        }
       }
     }
     __syncwarp();
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n");
     // ===================== softmax / correction / epilogue =====================
     const int q = (warp - 4) >> 2;  // Q tile of this warp group
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t s_addr = tmem_base + lane_off + (q ? C::S_COL1 : C::S_COL0);
-    const uint32_t o_addr = tmem_base + lane_off + (q ? C::O_COL1 : C::O_COL0);  // O (64) then L (16)
+    const uint32_t s_addr = tmem_base + lane_off + C::S_COL + q * 64;
+    const uint32_t o_addr = tmem_base + lane_off + C::O_COL + q * 64;
     const float c = p.scale_log2e;
+    const uint32_t p_row = smem_u32(sP + q * C::P_BYTES + r * 128);
+    const uint32_t sw = r & 7;
+
     float m_used = -INFINITY;  // maximum the exponent is taken against (raw score units)
-    uint8_t* p_row = sP + q * C::P_BYTES + r * 128;
-    const int sw = r & 7;
+    float l = 0.0f;            // running row sum of exp
 
     for (int j = 0; j < T; ++j) {
+      const bool tr = TRACE && r == 0 && j >= 16 && j < 24;
+      const int tb = (q * 8 + ((j - 16) & 7)) * 8;
+      if (tr) stamp(tb + 0);
       const bool seg1 = j >= T0;
-      const int row0 = (seg1 ? (j - T0) : j) * BKV;
-      const int nvalid = min(BKV, (seg1 ? p.n1 : p.n0) - row0);
+      const int nv = min(BKV, (seg1 ? p.n1 : p.n0) - (seg1 ? (j - T0) : j) * BKV);
+      // ---- scores of block j: TMEM -> registers, S released for Q.K(j+1)^T ----
+      uint32_t sv[2][32];
       mbar_wait(&s_full[q], j & 1);
       tc_fence_after();
-      float s[BKV];
-#pragma unroll
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(s_addr + c0, v);
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) s[c0 + jj] = __uint_as_float(v[jj]);
-      }
-      tmem_ld_wait();
+      if (tr) stamp(tb + 1);
+      tmem_ld_32x32b_x32(s_addr, sv[0]);
+      tmem_ld_32x32b_x32(s_addr + 32, sv[1]);
+      tmem_ld_wait_dep(sv[0]);
+      tmem_ld_wait_dep(sv[1]);
       tc_fence_before();
-      mbar_arrive(&s_free[q]);  // S_q may be overwritten by Q_q K(j+1)^T
-
-      if (nvalid < BKV) {
+      mbar_arrive(&s_free[q]);
+      if (tr) stamp(tb + 2);
+      if (nv < BKV) {  // ragged last block of a segment: keys past the end score -inf
 #pragma unroll
         for (int jj = 0; jj < BKV; ++jj)
-          if (jj >= nvalid) s[jj] = -INFINITY;
+          if (jj >= nv) sv[jj >> 5][jj & 31] = 0xff800000u;
       }
-      float m_tile = s[0];
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-      for (int jj = 1; jj < BKV; ++jj) m_tile = fmaxf(m_tile, s[jj]);
+      for (int jj = 0; jj < 32; jj += 2) {
+        m0 = fmaxf(m0, __uint_as_float(sv[0][jj]));
+        m1 = fmaxf(m1, __uint_as_float(sv[0][jj + 1]));
+        m2 = fmaxf(m2, __uint_as_float(sv[1][jj]));
+        m3 = fmaxf(m3, __uint_as_float(sv[1][jj + 1]));
+      }
+      const float m_blk = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       // lazy maximum: only move the reference when it grew by more than 8 in the exp2 domain
       float alpha = 1.0f;
-      if ((m_tile - m_used) * c > 8.0f) {
-        alpha = exp2_approx((m_used - m_tile) * c);  // first tile: 2^-inf = 0 (O is not read then)
-        m_used = m_tile;
+      if ((m_blk - m_used) * c > 8.0f) {
+        alpha = exp2_approx((m_used - m_blk) * c);  // first block: 2^-inf = 0 (l = 0, O is not read)
+        m_used = m_blk;
       }
       const float mc = m_used * c;
-      uint32_t pk[BKV / 2];
+      if (tr) stamp(tb + 3);
+      // ---- exponentials, packed to fp16 in place; row sum in fp32 ----
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      uint32_t pk[32];
 #pragma unroll
-      for (int jj = 0; jj < BKV; jj += 2)
-        pk[jj >> 1] = exp2_pack_h2(fmaf(s[jj], c, -mc), fmaf(s[jj + 1], c, -mc));
-
+      for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+        for (int u = 0; u < 16; u += 2) {
+          const float e0 = exp2_approx(fmaf(__uint_as_float(sv[hh][2 * u]), c, -mc));
+          const float e1 = exp2_approx(fmaf(__uint_as_float(sv[hh][2 * u + 1]), c, -mc));
+          const float e2 = exp2_approx(fmaf(__uint_as_float(sv[hh][2 * u + 2]), c, -mc));
+          const float e3 = exp2_approx(fmaf(__uint_as_float(sv[hh][2 * u + 3]), c, -mc));
+          sum0 += e0; sum1 += e1; sum2 += e2; sum3 += e3;
+          pk[hh * 16 + u] = pack_half2(e0, e1);
+          pk[hh * 16 + u + 1] = pack_half2(e2, e3);
+        }
+      }
+      l = fmaf(l, alpha, (sum0 + sum1) + (sum2 + sum3));
+      if (tr) stamp(tb + 4);
+      // ---- P buffer free (P.V(j-1) done); rare O rescale; P -> shared memory ----
       if (j > 0) {
-        mbar_wait(&pv_done[q], (j - 1) & 1);  // P buffer free, O/L quiescent
+        mbar_wait(&pv_done[q], (j - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+          // the reference maximum moved: O is scaled while no P.V of this tile is in flight
 #pragma unroll
-          for (int c0 = 0; c0 < 64; c0 += 32) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(o_addr + c0, o);
+          for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(o_addr + c0, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) o[jj] = __float_as_uint(__uint_as_float(o[jj]) * alpha);
-            tmem_st_32x32b_x32(o_addr + c0, o);
+            for (int jj = 0; jj < 16; ++jj) o[jj] = __float_as_uint(__uint_as_float(o[jj]) * alpha);
+            tmem_st_32x32b_x16(o_addr + c0, o);
           }
-          uint32_t l[16];
-          tmem_ld_32x32b_x16(o_addr + 64, l);
-          tmem_ld_wait();
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) l[jj] = __float_as_uint(__uint_as_float(l[jj]) * alpha);
-          tmem_st_32x32b_x16(o_addr + 64, l);
           tmem_st_wait();
         }
       }
+      if (tr) stamp(tb + 5);
+      // 64 keys of this row -> 128 B of the swizzled P tile (SWIZZLE_128B: 16-byte chunk i of row r
+      // sits at chunk i ^ (r & 7))
 #pragma unroll
-      for (int i = 0; i < BKV / 8; ++i) {
-        uint4 val = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-        uint8_t* dst = p_row + (i >> 3) * (BQ * 128) + (((i & 7) ^ sw) << 4);
-        *reinterpret_cast<uint4*>(dst) = val;
-      }
+      for (int i = 0; i < 8; ++i)
+        st_shared_v4(p_row + ((static_cast<uint32_t>(i) ^ sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2],
+                     pk[4 * i + 3]);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[q]);
+      if (tr) stamp(tb + 6);
     }
 
-    // epilogue: O / l -> fp16
+    // epilogue: O / l -> fp16 (UMMAs of one thread complete in order: the last P.V done = all done)
     mbar_wait(&pv_done[q], (T - 1) & 1);
     tc_fence_after();
-    uint32_t l[16];
-    tmem_ld_32x32b_x16(o_addr + 64, l);
-    tmem_ld_wait();
-    const float inv_l = 1.0f / __uint_as_float(l[0]);
+    const float inv_l = 1.0f / l;
     const int qrow = q0 + q * BQ + r;
     const bool row_ok = qrow < p.nq;
     __half* orow = p.out + ((long)b * p.nq + qrow) * p.out_ld + h * D;
@@ -357,7 +419,23 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+  if (TRACE && traced && threadIdx.x == 0) {
+    const uint32_t t0 = trace_buf[0];
+    for (int q = 0; q < 2; ++q)
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t* tr = trace_buf + (q * 8 + j) * 8;
+        printf("smx q=%d j=%2d: start %6u | S ready +%4u | S in regs +%4u | max/alpha +%4u | exps done +%4u | P free +%4u "
+               "| p_full +%4u\n", q, j + 16, tr[0] - t0, tr[1] - tr[0], tr[2] - tr[0], tr[3] - tr[0], tr[4] - tr[0],
+               tr[5] - tr[0], tr[6] - tr[0]);
+      }
+    for (int q = 0; q < 2; ++q)
+      for (int n = 0; n < 8; ++n) {
+        const uint32_t* tr = trace_buf + 128 + (q * 8 + n) * 4;
+        printf("mma q=%d n=%2d: QK issue %6u (+%3u) | PV issue %6u (+%3u)\n", q, n + 16, tr[0] - t0, tr[1] - tr[0],
+               tr[2] - t0, tr[3] - tr[2]);
+      }
   }
 }
 
@@ -393,14 +471,17 @@ int attention_v2_d40(const idiff_attn_args* a, cudaStream_t stream) {
   p.scale_log2e = a->scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__half*>(a->out);
   p.out_ld = a->out_ld;
+  static const bool trace = getenv("IDIFF_ATT2_TRACE") != nullptr;
+  auto kern = trace ? attention2_kernel<D, true> : attention2_kernel<D, false>;
+  const int smem_bytes = C::SMEM_BYTES + (trace ? C::TRACE_BYTES : 0);
   static bool attr_set = false;
   if (!attr_set) {
-    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(attention2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          C::SMEM_BYTES));
+    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   dim3 grid((a->nq + 2 * BQ - 1) / (2 * BQ), a->heads, a->batch);
-  attention2_kernel<D><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmK0, tmV0, tmK1, tmV1, p);
+  kern<<<grid, THREADS, smem_bytes, stream>>>(tmQ, tmK0, tmV0, tmK1, tmV1, p);
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

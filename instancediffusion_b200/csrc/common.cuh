@@ -56,6 +56,19 @@ IDIFF_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a system-defined time; a polling loop over
+// several barriers wants the immediate answer).
+IDIFF_DEVICE bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a trapped launch (an error code at the C ABI),
 // never as a hung GPU.  ~4 s at 2 GHz.
 IDIFF_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
