@@ -94,14 +94,6 @@ IDIFF_DEVICE void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t 
                : "memory");
 }
 
-// ptxas schedules within basic blocks and, left alone, hoists every MUFU of a block above the TMEM
-// traffic that should overlap with it (the PTX order is not kept).  A never-taken, data-dependent
-// branch ends the basic block and pins the order of the pieces on either side.  0xffffffff is not a
-// value F2FP can produce (NaN packs as 0x7fff), so the trap is unreachable.
-IDIFF_DEVICE void sched_fence(uint32_t packed) {
-  if (packed == 0xffffffffu) asm volatile("trap;\n");
-}
-
 // TRACE (IDIFF_ATT2_TRACE=1): one CTA records clock stamps of blocks 16..23 in shared memory and prints
 // them at exit -- a timeline of the hand-offs that costs the measured kernel nothing but a few STS.
 template <int D, bool TRACE = false>

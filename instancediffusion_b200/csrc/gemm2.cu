@@ -116,6 +116,14 @@ struct WorkIter {
   }
 };
 
+IDIFF_DEVICE void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 IDIFF_DEVICE void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -312,6 +320,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tile_origin(sg.tile, n0, m0, b0, h0, w0);
       const bool owner = sg.kb0 == 0;
       const bool complete = owner && sg.kb1 == p.KB;
+      const bool fixup = owner && !complete;  // this CTA holds the tile's first k-blocks, others the rest
       // followers of an incomplete owner segment: the CTAs covering the tile's remaining k-blocks
       int f0 = 0, f1 = -1;
       if (owner && !complete) {
@@ -426,10 +435,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           uint32_t v[CHUNK];
           tmem_ld_32x32b_x16(trow + c0, v);
           tmem_ld_wait();
-          float4* dst = reinterpret_cast<float4*>(wsb + ((long)(c0 / CHUNK) * 128 + r) * CHUNK);
+          // layout [chunk][quad q][row][4 floats]: one warp instruction covers 512 contiguous bytes
+          // (16 full sectors); row-major 64-byte rows made every lane touch its own half sector and the
+          // owner's fold was bound by L2 transactions, not bytes
+          float4* dst = reinterpret_cast<float4*>(wsb) + (long)(c0 / CHUNK) * 4 * 128 + r;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            __stcg(dst + q, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+            __stcg(dst + q * 128, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
                                         __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])));
         }
         tc_fence_before();
@@ -440,7 +452,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) st_release_gpu(p.sflags + cta * EPI_WARPS + ew, 1);
       } else {
         // ---- owner: (optional fixup) + fused epilogue ----
-        if (!complete) {
+        if (fixup) {
           for (int f = f0; f <= f1; ++f) {
             const int* fl = p.sflags + f * EPI_WARPS + ew;
             const long long t0 = clock64();
@@ -451,6 +463,54 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
             }
           }
+                  // Fold the followers' partial tiles into this CTA's accumulator in TMEM, in CTA order (the sum
+          // is bit-reproducible), with up to FB x 4 independent 16-byte loads in flight per thread.  The
+          // first version added the partials inside the epilogue's chunk loop, one dependent L2 round
+          // trip per follower and chunk: with seven followers (3x3 convolutions at 8x8) the owners'
+          // epilogue took 35 us of a 68 us kernel (tools/trace_gemm.py conv1280_8).  After this pass
+          // the epilogue variants below see a complete accumulator.
+          constexpr int FB = 4;
+          const long fstride = (long)(BN / CHUNK) * 128 * CHUNK;
+#pragma unroll 1
+          for (int ch = 0; ch < NCH; ++ch) {
+            const int c0 = chunk_col(ch);
+            uint32_t av[CHUNK];
+            tmem_ld_32x32b_x16(trow + c0, av);
+            const float4* base = reinterpret_cast<const float4*>(p.ws) + (long)(c0 / CHUNK) * 4 * 128 + r;
+            float a[CHUNK];
+            bool first = true;
+            for (int fb = f0; fb <= f1; fb += FB) {
+              float4 tq[FB][4];
+#pragma unroll
+              for (int k = 0; k < FB; ++k) {
+                if (fb + k <= f1) {
+                  const float4* src = base + (long)(fb + k) * (fstride / 4);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) tq[k][q] = __ldcg(src + q * 128);
+                }
+              }
+              if (first) {
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j) a[j] = __uint_as_float(av[j]);
+                first = false;
+              }
+#pragma unroll
+              for (int k = 0; k < FB; ++k) {
+                if (fb + k <= f1) {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    a[4 * q] += tq[k][q].x; a[4 * q + 1] += tq[k][q].y;
+                    a[4 * q + 2] += tq[k][q].z; a[4 * q + 3] += tq[k][q].w;
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) av[j] = __float_as_uint(a[j]);
+            tmem_st_32x32b_x16(trow + c0, av);
+          }
+          tmem_st_wait();
         }
         // Lean epilogue: all per-tile pointers are formed once, bias / row-add / residual arrive as
         // 16-byte vector loads per 16-column chunk, and mode switches are warp-uniform branches
@@ -495,21 +555,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 x[j] = __uint_as_float(v[j]);
                 gx[j] = __uint_as_float(g[j]);
               }
-              if (!complete) {
-                for (int f = f0; f <= f1; ++f) {
-                  const float* wsf = p.ws + (long)f * (BN / CHUNK) * 128 * CHUNK;
-                  const float4* src = reinterpret_cast<const float4*>(wsf + ((long)(c0 / CHUNK) * 128 + r) * CHUNK);
-                  const float4* srcg = reinterpret_cast<const float4*>(
-                      wsf + ((long)((BN / 2 + c0) / CHUNK) * 128 + r) * CHUNK);
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const float4 t = __ldcg(src + q);
-                    const float4 u = __ldcg(srcg + q);
-                    x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
-                    gx[4 * q] += u.x; gx[4 * q + 1] += u.y; gx[4 * q + 2] += u.z; gx[4 * q + 3] += u.w;
-                  }
-                }
-              }
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 float bv[4], bg[4];
@@ -522,17 +567,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < CHUNK; ++j) x[j] = __uint_as_float(v[j]);
-              if (!complete) {
-                for (int f = f0; f <= f1; ++f) {
-                  const float* wsf = p.ws + (long)f * (BN / CHUNK) * 128 * CHUNK;
-                  const float4* src = reinterpret_cast<const float4*>(wsf + ((long)(c0 / CHUNK) * 128 + r) * CHUNK);
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const float4 t = __ldcg(src + q);
-                    x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
-                  }
-                }
-              }
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 float bv[4];
@@ -616,17 +650,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             float x[CHUNK];
 #pragma unroll
             for (int j = 0; j < CHUNK; ++j) x[j] = __uint_as_float(xv[i][j]);
-            if (!complete) {
-              for (int f = f0; f <= f1; ++f) {
-                const float* wsf = p.ws + (long)f * (BN / CHUNK) * 128 * CHUNK;
-                const float4* src = reinterpret_cast<const float4*>(wsf + ((long)(c0 / CHUNK) * 128 + r) * CHUNK);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float4 t = __ldcg(src + q);
-                  x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
-                }
-              }
-            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 bv = *(reinterpret_cast<const float4*>(tab_row + c0) + q);
@@ -636,18 +659,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               float gx[CHUNK];
 #pragma unroll
               for (int j = 0; j < CHUNK; ++j) gx[j] = __uint_as_float(gv[geglu ? i : 0][j]);
-              if (!complete) {
-                for (int f = f0; f <= f1; ++f) {
-                  const float* wsf = p.ws + (long)f * (BN / CHUNK) * 128 * CHUNK;
-                  const float4* srcg = reinterpret_cast<const float4*>(
-                      wsf + ((long)((BN / 2 + c0) / CHUNK) * 128 + r) * CHUNK);
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const float4 u = __ldcg(srcg + q);
-                    gx[4 * q] += u.x; gx[4 * q + 1] += u.y; gx[4 * q + 2] += u.z; gx[4 * q + 3] += u.w;
-                  }
-                }
-              }
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const float4 bg = *(reinterpret_cast<const float4*>(tab_row + BN / 2 + c0) + q);
@@ -769,7 +780,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (sc == 0 && threadIdx.x == 128) stamp(5);
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
-        if (!complete) {
+        if (fixup) {
           // consume the followers' flags so the next launch (or graph replay) starts clean
           __syncwarp();
           if (lane == 0)
@@ -816,24 +827,8 @@ static void choose_patch(int H, int W, int* PW, int* PH, int* PB) {
   *PB = 128 / (pw * ph);
 }
 
-static int pick_bn(int N, bool geglu) {
-  if (geglu || N <= 128) return 128;
-  const int cands[4] = {256, 192, 160, 128};
-  int best = 128;
-  long best_pad = -1;
-  for (int i = 0; i < 4; ++i) {
-    const int bn = cands[i];
-    const long pad = (long)((N + bn - 1) / bn) * bn;
-    if (best_pad < 0 || pad < best_pad) {
-      best_pad = pad;
-      best = bn;
-    }
-  }
-  return best;
-}
-
 template <int BN, int MODE, bool TMA_EPI>
-static int launch(const idiff_gemm_args* a, cudaStream_t stream) {
+static int launch(const idiff_gemm_args* a, cudaStream_t stream, bool want_sk) {
   using C = Cfg<BN, TMA_EPI>;
   Params p;
   memset(&p, 0, sizeof(p));
@@ -899,7 +894,7 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream) {
   // Stream-K needs the fixup workspace (flags in its first 64 KiB, partial tiles after); short-K
   // problems (fixup cost ~ mainloop) and exact multiples of the SM count stay data-parallel.
   const long ws_need = kFlagBytes + (long)g_num_sms * 128 * BN * sizeof(float);
-  const bool use_sk = g_ws && g_ws_bytes >= ws_need && p.KB >= 8 && (p.T % g_num_sms) != 0 &&
+  const bool use_sk = want_sk && g_ws && g_ws_bytes >= ws_need && p.KB >= 8 && (p.T % g_num_sms) != 0 &&
                       (long)p.T * p.KB >= g_num_sms;
   if (use_sk) {
     p.G = g_num_sms;
@@ -946,20 +941,99 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream) {
   return 0;
 }
 
+// Tile width and schedule.  A small cost model in SM clocks, calibrated on tools/bench_kernels.py and
+// tools/trace_gemm.py at the UNet's shapes:
+//   * one 64-deep k-block of a 128 x BN tile costs max(UMMA time 2*BN, operand bytes / ~50 B/clk/SM);
+//   * data-parallel: ceil(T / SMs) rounds of (KB k-blocks + ~600 clk of pipeline fill) and one exposed
+//     epilogue (~1000 clk per 32 columns);
+//   * stream-K: the k-blocks of the last partial round are spread evenly, but the fixup is expensive --
+//     ~30k clk of flag / partial-tile round trips plus the owner pulling every follower's fp32 tile
+//     through one SM's L2 port (~40 B/clk).  It only wins for long-K tiles (3x3 convolutions at the
+//     16x16 / 8x8 levels); for K <= 2560 it was 10-20 us slower than two plain rounds.
+struct Plan {
+  int bn;
+  bool sk;
+};
+static int count_m_tiles(const idiff_gemm_args* a) {
+  if (a->conv_h > 0) {
+    int pw, ph, pb;
+    choose_patch(a->conv_h, a->conv_w, &pw, &ph, &pb);
+    return (a->conv_w / pw) * ((a->conv_h + ph - 1) / ph) * ((a->conv_b + pb - 1) / pb);
+  }
+  return (a->M + BM - 1) / BM;
+}
+static Plan plan_gemm(const idiff_gemm_args* a, bool fixed_bn128) {
+  const char* force = getenv("IDIFF_GEMM_PLAN");  // "bn,sk" overrides the model (tests, tuning); bn 0 = keep
+  if (g_num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  const int sms = g_num_sms;
+  const int KB = (a->K + BK - 1) / BK;
+  const int m_tiles = count_m_tiles(a);
+  const int cands[4] = {256, 192, 160, 128};
+  long min_pad = -1;
+  for (int i = 0; i < 4; ++i) {
+    const long pad = (long)((a->N + cands[i] - 1) / cands[i]) * cands[i];
+    if (min_pad < 0 || pad < min_pad) min_pad = pad;
+  }
+  Plan best = {128, false};
+  double best_cost = -1;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (fixed_bn128 && bn != 128) continue;
+    if (!fixed_bn128 && a->N <= 128 && bn != 128) continue;
+    const long pad = (long)((a->N + bn - 1) / bn) * bn;
+    if (!fixed_bn128 && pad > min_pad + min_pad / 14) continue;  // more than ~7 % wasted columns
+    const long T = (long)((a->N + bn - 1) / bn) * m_tiles;
+    const double t_kb = fmax(2.0 * bn, (16384.0 + 128.0 * bn) / 50.0);
+    const double t_epi = 1000.0 * bn / 32.0;
+    const double t_tile = KB * t_kb + 600.0;
+    const long rounds = (T + sms - 1) / sms;
+    const double cost_dp = rounds * t_tile + t_epi;
+    if (best_cost < 0 || cost_dp < best_cost) {
+      best_cost = cost_dp;
+      best = {bn, false};
+    }
+    if (KB >= 8 && (T % sms) != 0 && T * KB >= sms) {
+      const long full = T / sms;
+      const long t_dp = full >= 2 ? (full - 1) * sms : 0;
+      const long t_sk = T - t_dp;
+      const double followers = t_sk < sms ? (double)(sms - t_sk) / t_sk : 1.0;
+      const double cost_sk = (full >= 2 ? (full - 1) : 0) * t_tile + (double)t_sk * KB / sms * t_kb + t_epi + 30000.0 +
+                             followers * 128.0 * bn * 4.0 / 40.0;
+      if (cost_sk < best_cost) {
+        best_cost = cost_sk;
+        best = {bn, true};
+      }
+    }
+  }
+  if (force) {
+    int fbn = 0, fsk = 0;
+    if (sscanf(force, "%d,%d", &fbn, &fsk) == 2) {
+      if (!fixed_bn128 && (fbn == 256 || fbn == 192 || fbn == 160 || fbn == 128)) best.bn = fbn;
+      best.sk = fsk != 0;
+    }
+  }
+  return best;
+}
+
 // One instantiation per (tile width, epilogue mode): the epilogue is fully unrolled over its
 // column chunks, so each kernel carries only its own mode's code (an all-modes kernel was ~140 KB
 // of SASS and stalled on instruction fetch: 26 % stall_no_inst, profiles/).
 int gemm_v2(const idiff_gemm_args* a, cudaStream_t stream) {
-  if (a->flags & IDIFF_EPI_GEGLU) return launch<128, MODE_GEGLU, true>(a, stream);
-  if (a->flags & IDIFF_OUT_F32_NCHW) return launch<128, MODE_NCHW, false>(a, stream);
+  if (a->flags & IDIFF_EPI_GEGLU) return launch<128, MODE_GEGLU, true>(a, stream, plan_gemm(a, true).sk);
+  if (a->flags & IDIFF_OUT_F32_NCHW) return launch<128, MODE_NCHW, false>(a, stream, plan_gemm(a, true).sk);
   // short K: the epilogue dominates -> TMA-staged epilogue (shallower operand ring);
   // long K (3x3 convolutions): deep operand ring, direct epilogue hidden behind the next mainloop
   const bool tma_epi = ((a->K + BK - 1) / BK) <= kTmaEpiMaxKB;
-  switch (pick_bn(a->N, false)) {
-    case 256: return tma_epi ? launch<256, MODE_PLAIN, true>(a, stream) : launch<256, MODE_PLAIN, false>(a, stream);
-    case 192: return tma_epi ? launch<192, MODE_PLAIN, true>(a, stream) : launch<192, MODE_PLAIN, false>(a, stream);
-    case 160: return tma_epi ? launch<160, MODE_PLAIN, true>(a, stream) : launch<160, MODE_PLAIN, false>(a, stream);
-    default: return tma_epi ? launch<128, MODE_PLAIN, true>(a, stream) : launch<128, MODE_PLAIN, false>(a, stream);
+  const Plan pl = plan_gemm(a, false);
+  switch (pl.bn) {
+    case 256: return tma_epi ? launch<256, MODE_PLAIN, true>(a, stream, pl.sk) : launch<256, MODE_PLAIN, false>(a, stream, pl.sk);
+    case 192: return tma_epi ? launch<192, MODE_PLAIN, true>(a, stream, pl.sk) : launch<192, MODE_PLAIN, false>(a, stream, pl.sk);
+    case 160: return tma_epi ? launch<160, MODE_PLAIN, true>(a, stream, pl.sk) : launch<160, MODE_PLAIN, false>(a, stream, pl.sk);
+    default: return tma_epi ? launch<128, MODE_PLAIN, true>(a, stream, pl.sk) : launch<128, MODE_PLAIN, false>(a, stream, pl.sk);
   }
 }
 

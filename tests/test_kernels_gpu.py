@@ -3,6 +3,7 @@ on the same seeded inputs (the fp16-rounded inputs are upcast, so only accumulat
 fp16 output rounding differ).  Tolerances are stated per test.
 """
 import math
+import os
 
 import pytest
 import torch
@@ -61,12 +62,22 @@ def test_gemm_stream_k_shapes(cuda_device, M, N, K):
     w = _randn((N, K), cuda_device, 1.0 / math.sqrt(K), 2).half()
     bias = _randn((N,), cuda_device, 0.5, 3)
     res = _randn((M, N), cuda_device, 1.0, 4).half()
-    out = ops.gemm(a, w, bias, residual=res, gate=0.5)
     ref = res.float() + 0.5 * (a.float() @ w.float().t() + bias)
-    _check(out, ref, 2e-3, 2e-3, f"gemm stream-K {M}x{N}x{K}")
-    for _ in range(3):
-        again = ops.gemm(a, w, bias, residual=res, gate=0.5)
-        assert torch.equal(out, again), "stream-K result is not bit-reproducible"
+    # the planner may prefer plain rounds for a shape; IDIFF_GEMM_PLAN="0,1" keeps its tile width and
+    # forces the stream-K schedule, so both paths are covered
+    for plan in (None, "0,1"):
+        if plan is None:
+            os.environ.pop("IDIFF_GEMM_PLAN", None)
+        else:
+            os.environ["IDIFF_GEMM_PLAN"] = plan
+        try:
+            out = ops.gemm(a, w, bias, residual=res, gate=0.5)
+            _check(out, ref, 2e-3, 2e-3, f"gemm stream-K {M}x{N}x{K} plan={plan}")
+            for _ in range(3):
+                again = ops.gemm(a, w, bias, residual=res, gate=0.5)
+                assert torch.equal(out, again), "stream-K result is not bit-reproducible"
+        finally:
+            os.environ.pop("IDIFF_GEMM_PLAN", None)
 
 
 def test_gemm_geglu_stream_k(cuda_device):
@@ -77,11 +88,16 @@ def test_gemm_geglu_stream_k(cuda_device):
     w = _randn((8 * C, C), cuda_device, 1.0 / math.sqrt(C), 2).half()
     bias = _randn((8 * C,), cuda_device, 0.5, 3)
     wp, bp = pack_geglu(w, bias)
-    out = ops.gemm(a, wp, bp, geglu=True)
     h = a.float() @ w.float().t() + bias
     x, gate = h.chunk(2, dim=-1)
-    _check(out, x * F.gelu(gate), 3e-3, 3e-3, "geglu stream-K 2048x1280")
-    assert torch.equal(out, ops.gemm(a, wp, bp, geglu=True))
+    os.environ["IDIFF_GEMM_PLAN"] = "0,1"  # force the stream-K schedule (see above)
+    try:
+        out = ops.gemm(a, wp, bp, geglu=True)
+        _check(out, x * F.gelu(gate), 3e-3, 3e-3, "geglu stream-K 2048x1280")
+        assert torch.equal(out, ops.gemm(a, wp, bp, geglu=True))
+    finally:
+        os.environ.pop("IDIFF_GEMM_PLAN", None)
+    _check(ops.gemm(a, wp, bp, geglu=True), x * F.gelu(gate), 3e-3, 3e-3, "geglu planned 2048x1280")
 
 
 def test_gemm_residual_gate_silu(cuda_device):

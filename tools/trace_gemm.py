@@ -17,6 +17,8 @@ shapes = {
     "qkv320": lambda: (r(B * 4096, 320), r(960, 320, sc=0.05), dict()),
     "ff2_640": lambda: (r(B * 1024, 2560), r(640, 2560, sc=0.02), dict(residual=r(B * 1024, 640))),
     "conv1280": lambda: (r(B * 256, 1280), r(1280, 11520, sc=0.01), dict(conv=(B, 16, 16, 1280), residual=r(B * 256, 1280))),
+    "conv1280_8": lambda: (r(B * 64, 1280), r(1280, 11520, sc=0.01), dict(conv=(B, 8, 8, 1280), residual=r(B * 64, 1280))),
+    "ff2_1280_8": lambda: (r(B * 64, 5120), r(1280, 5120, sc=0.02), dict(residual=r(B * 64, 1280))),
     "conv320": lambda: (r(B * 4096, 320), r(320, 2880, sc=0.02), dict(conv=(B, 64, 64, 320), residual=r(B * 4096, 320))),
 }
 names = ["entry", "1st tile", "seg0 issued", "acc0 ready", "fixup done", "epi0 done", "loops done", "exit",
