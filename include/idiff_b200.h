@@ -39,7 +39,7 @@ int idiff_version(void);
  * tap by tap with 4-D TMA boxes and hardware zero fill at the borders (no im2col buffer);
  * W is [N, 9*conv_cin] with k = (ky*3+kx)*conv_cin + c; stride 1, padding 1.
  * ------------------------------------------------------------------------------------------- */
-#define IDIFF_EPI_GEGLU 1       /* W rows interleaved per 64: [value(64) | gate(64)]; out has N/2 cols:
+#define IDIFF_EPI_GEGLU 1       /* W rows interleaved per 128: [value(128) | gate(128)]; out has N/2 cols:
                                    (value+b)*gelu_erf(gate+b)            (attention.py:41-43)   */
 #define IDIFF_EPI_SILU 2        /* x -> x*sigmoid(x) after bias                                   */
 #define IDIFF_OUT_F32_NCHW 4    /* out is fp32 (B, N, H*W): the eps layout the samplers consume   */

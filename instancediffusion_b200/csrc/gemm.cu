@@ -350,7 +350,7 @@ extern "C" int idiff_gemm(const idiff_gemm_args* a, void* stream) {
   const bool geglu = (a->flags & IDIFF_EPI_GEGLU) != 0;
   const bool nchw = (a->flags & IDIFF_OUT_F32_NCHW) != 0;
   if (geglu) {
-    IDIFF_REQUIRE(a->N % 128 == 0, "idiff_gemm: GEGLU needs N %% 128 == 0 (N=%d)", a->N);
+    IDIFF_REQUIRE(a->N % 256 == 0, "idiff_gemm: GEGLU needs N %% 256 == 0 (N=%d)", a->N);
     IDIFF_REQUIRE(!a->residual && !a->rowadd && !nchw, "idiff_gemm: GEGLU excludes residual/rowadd/NCHW");
   }
   if (!nchw) {
@@ -366,10 +366,11 @@ extern "C" int idiff_gemm(const idiff_gemm_args* a, void* stream) {
   }
   // gemm2.cu (persistent / stream-K / wide tiles) is the production kernel; the first-generation
   // kernel in this file stays selectable for A/B measurements (IDIFF_GEMM_V1=1).
-  static const bool use_v1 = []() {
+  static const bool use_v1_env = []() {
     const char* e = getenv("IDIFF_GEMM_V1");
     return e && e[0] == '1';
   }();
+  const bool use_v1 = use_v1_env && !geglu;  // the v1 kernel's 128-wide tiles predate the 128-row GEGLU groups
   if (use_v1) return launch_gemm<128>(a, reinterpret_cast<cudaStream_t>(stream));
   return v2::gemm_v2(a, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -962,7 +962,7 @@ static int count_m_tiles(const idiff_gemm_args* a) {
   }
   return (a->M + BM - 1) / BM;
 }
-static Plan plan_gemm(const idiff_gemm_args* a, bool fixed_bn128) {
+static Plan plan_gemm(const idiff_gemm_args* a, int fixed_bn) {  // fixed_bn: 0 = choose the tile width
   const char* force = getenv("IDIFF_GEMM_PLAN");  // "bn,sk" overrides the model (tests, tuning); bn 0 = keep
   if (g_num_sms == 0) {
     int dev = 0;
@@ -978,14 +978,14 @@ static Plan plan_gemm(const idiff_gemm_args* a, bool fixed_bn128) {
     const long pad = (long)((a->N + cands[i] - 1) / cands[i]) * cands[i];
     if (min_pad < 0 || pad < min_pad) min_pad = pad;
   }
-  Plan best = {128, false};
+  Plan best = {fixed_bn ? fixed_bn : 128, false};
   double best_cost = -1;
   for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
-    if (fixed_bn128 && bn != 128) continue;
-    if (!fixed_bn128 && a->N <= 128 && bn != 128) continue;
+    if (fixed_bn && bn != fixed_bn) continue;
+    if (!fixed_bn && a->N <= 128 && bn != 128) continue;
     const long pad = (long)((a->N + bn - 1) / bn) * bn;
-    if (!fixed_bn128 && pad > min_pad + min_pad / 14) continue;  // more than ~7 % wasted columns
+    if (!fixed_bn && pad > min_pad + min_pad / 14) continue;  // more than ~7 % wasted columns
     const long T = (long)((a->N + bn - 1) / bn) * m_tiles;
     const double t_kb = fmax(2.0 * bn, (16384.0 + 128.0 * bn) / 50.0);
     const double t_epi = 1000.0 * bn / 32.0;
@@ -1012,7 +1012,7 @@ static Plan plan_gemm(const idiff_gemm_args* a, bool fixed_bn128) {
   if (force) {
     int fbn = 0, fsk = 0;
     if (sscanf(force, "%d,%d", &fbn, &fsk) == 2) {
-      if (!fixed_bn128 && (fbn == 256 || fbn == 192 || fbn == 160 || fbn == 128)) best.bn = fbn;
+      if (!fixed_bn && (fbn == 256 || fbn == 192 || fbn == 160 || fbn == 128)) best.bn = fbn;
       best.sk = fsk != 0;
     }
   }
@@ -1023,8 +1023,9 @@ static Plan plan_gemm(const idiff_gemm_args* a, bool fixed_bn128) {
 // column chunks, so each kernel carries only its own mode's code (an all-modes kernel was ~140 KB
 // of SASS and stalled on instruction fetch: 26 % stall_no_inst, profiles/).
 int gemm_v2(const idiff_gemm_args* a, cudaStream_t stream) {
-  if (a->flags & IDIFF_EPI_GEGLU) return launch<128, MODE_GEGLU, true>(a, stream, plan_gemm(a, true).sk);
-  if (a->flags & IDIFF_OUT_F32_NCHW) return launch<128, MODE_NCHW, false>(a, stream, plan_gemm(a, true).sk);
+  // GEGLU: one 256-column accumulator tile = 128 value columns + their 128 gates (packing.py)
+  if (a->flags & IDIFF_EPI_GEGLU) return launch<256, MODE_GEGLU, true>(a, stream, plan_gemm(a, 256).sk);
+  if (a->flags & IDIFF_OUT_F32_NCHW) return launch<128, MODE_NCHW, false>(a, stream, plan_gemm(a, 128).sk);
   // short K: the epilogue dominates -> TMA-staged epilogue (shallower operand ring);
   // long K (3x3 convolutions): deep operand ring, direct epilogue hidden behind the next mainloop
   const bool tma_epi = ((a->K + BK - 1) / BK) <= kTmaEpiMaxKB;

@@ -6,6 +6,9 @@ from typing import Optional, Tuple
 import torch
 
 
+GEGLU_GROUP = 128  # rows per value / gate group of a packed GEGLU projection (csrc/gemm2.cu: BN = 256)
+
+
 def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
     """(Cout, Cin, 3, 3) -> (Cout, 9*Cin) with k = (ky*3 + kx)*Cin + c: the K order in which the
     implicit-GEMM kernel walks the taps (csrc/gemm.cu)."""
@@ -21,19 +24,20 @@ def pack_conv1x1(w: torch.Tensor) -> torch.Tensor:
 
 def pack_geglu(w: torch.Tensor, bias: Optional[torch.Tensor]) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """GEGLU.proj (attention.py:39): rows [0, inner) are the value half and [inner, 2*inner) the
-    gate half (chunk(2, dim=-1), :42).  Interleave them per 64 so that one 128-column accumulator
-    tile holds value columns [0,64) and their gates [64,128) -- the GEGLU epilogue then needs a
-    single tile."""
+    gate half (chunk(2, dim=-1), :42).  Interleave them per GEGLU_GROUP = 128 so that one 256-column
+    accumulator tile holds value columns [0,128) and their gates [128,256) -- the GEGLU epilogue then
+    needs a single tile."""
     two_inner = w.shape[0]
     inner = two_inner // 2
-    assert inner % 64 == 0, "GEGLU inner dim must be a multiple of 64"
-    t = inner // 64
-    wv = w[:inner].reshape(t, 64, -1)
-    wg = w[inner:].reshape(t, 64, -1)
+    g = GEGLU_GROUP
+    assert inner % g == 0, f"GEGLU inner dim must be a multiple of {g}"
+    t = inner // g
+    wv = w[:inner].reshape(t, g, -1)
+    wg = w[inner:].reshape(t, g, -1)
     wp = torch.stack([wv, wg], dim=1).reshape(two_inner, -1).contiguous()
     bp = None
     if bias is not None:
-        bv = bias[:inner].reshape(t, 64)
-        bg = bias[inner:].reshape(t, 64)
+        bv = bias[:inner].reshape(t, g)
+        bg = bias[inner:].reshape(t, g)
         bp = torch.stack([bv, bg], dim=1).reshape(two_inner).contiguous()
     return wp, bp

@@ -71,7 +71,8 @@ def test_bad_arguments_are_reported_not_crashed():
 # ------------------------------------------------------------------------------------------------
 def test_pack_geglu_is_a_row_permutation():
     from instancediffusion_b200.packing import pack_geglu
-    C, inner = 16, 128
+    from instancediffusion_b200.packing import GEGLU_GROUP as G
+    C, inner = 16, 256
     w = torch.randn(2 * inner, C)
     b = torch.randn(2 * inner)
     wp, bp = pack_geglu(w, b)
@@ -79,7 +80,7 @@ def test_pack_geglu_is_a_row_permutation():
     h = x @ w.t() + b
     ref = h[:, :inner] * torch.nn.functional.gelu(h[:, inner:])
     hp = x @ wp.t() + bp
-    tiles = hp.view(5, inner // 64, 2, 64)
+    tiles = hp.view(5, inner // G, 2, G)
     got = (tiles[:, :, 0] * torch.nn.functional.gelu(tiles[:, :, 1])).reshape(5, inner)
     assert torch.allclose(got, ref, atol=1e-6)
 
