@@ -107,6 +107,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel (host.cuh launch_pdl)
+  pdl_wait();               // operands come from earlier kernels: nothing above touched global memory
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -336,7 +338,7 @@ static int launch_attention(const idiff_attn_args* a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((a->nq + BQ - 1) / BQ, a->heads, a->batch);
-  attention_kernel<D><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK0, tmV0, tmK1, tmV1, p);
+  IDIFF_CHECK_CUDA(launch_pdl(attention_kernel<D>, dim3(grid), dim3(ATT_THREADS), Cfg::SMEM_BYTES, stream, tmQ, tmK0, tmV0, tmK1, tmV1, p));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

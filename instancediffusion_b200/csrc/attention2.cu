@@ -128,6 +128,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (TRACE && traced) trace_buf[slot] = clock();
   };
 
+  pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel (host.cuh launch_pdl)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 2 * BQ;
@@ -160,6 +161,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // Q / K / V come from the previous kernel: nothing above touched global memory
 
   // Register re-partition between warpgroups (the setmaxnreg must sit at the head of each role
   // branch so that ptxas allocates the branch bodies against the new limits).
@@ -473,7 +475,7 @@ int attention_v2_d40(const idiff_attn_args* a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((a->nq + 2 * BQ - 1) / (2 * BQ), a->heads, a->batch);
-  kern<<<grid, THREADS, smem_bytes, stream>>>(tmQ, tmK0, tmV0, tmK1, tmV1, p);
+  IDIFF_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), smem_bytes, stream, tmQ, tmK0, tmV0, tmK1, tmV1, p));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

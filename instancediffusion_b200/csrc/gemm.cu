@@ -103,6 +103,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel (host.cuh launch_pdl)
+  pdl_wait();               // operands come from earlier kernels: nothing above touched global memory
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -336,7 +338,7 @@ static int launch_gemm(const idiff_gemm_args* a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid(n_tiles, m_tiles, 1);
-  gemm_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  IDIFF_CHECK_CUDA(launch_pdl(gemm_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, p));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -197,6 +197,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel (host.cuh launch_pdl)
+  pdl_wait();               // operands come from earlier kernels: nothing above touched global memory
   auto stamp = [&](int slot) {
     if (p.trace) {
       unsigned long long t;
@@ -936,7 +938,7 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream, bool want_sk) {
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  gemm2_kernel<BN, MODE, TMA_EPI><<<p.G, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmR, p);
+  IDIFF_CHECK_CUDA(launch_pdl(gemm2_kernel<BN, MODE, TMA_EPI>, dim3(p.G), dim3(THREADS), C::SMEM_BYTES, stream, tmA, tmB, tmO, tmR, p));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

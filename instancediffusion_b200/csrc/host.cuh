@@ -31,4 +31,28 @@ int encode_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t
 int encode_tmap_f16_sw(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                        const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
+// Launch with programmatic stream serialization ("programmatic dependent launch"): the kernel may
+// become resident while its predecessor in the stream is still running; every kernel of this library
+// calls pdl_wait() (common.cuh) before it touches global memory, so only launch latency and prologues
+// (barrier init, TMEM allocation, descriptor prefetch) overlap.  About 500 dependent launches make one
+// UNet forward.  Opt-in with IDIFF_PDL=1: measured neutral inside the CUDA graph (the big kernels fill
+// the register file, so a successor cannot become resident before they exit); plain stream order is
+// the default.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace idiff

@@ -32,6 +32,8 @@ IDIFF_DEVICE void unpack8(const uint4& v, float (&f)[8]) {
 __global__ void __launch_bounds__(512)
 gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int hw, int C, int groups,
                 int pix_per_block, int k) {
+  pdl_launch_dependents();  // programmatic dependent launch: the next kernel may start its prologue
+  pdl_wait();               // ... and this one touches global memory only after its predecessor finished
   extern __shared__ float red[];  // [k][C][2]
   const int CV = C >> 3;
   const int r = threadIdx.x / CV;
@@ -102,6 +104,8 @@ __global__ void __launch_bounds__(512)
 gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ gamma,
                 const float* __restrict__ beta, const float* __restrict__ partial, int hw, int C,
                 int groups, float eps, int fuse_silu, int pix_per_block, int k, int stat_chunks) {
+  pdl_launch_dependents();  // programmatic dependent launch: the next kernel may start its prologue
+  pdl_wait();               // ... and this one touches global memory only after its predecessor finished
   __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
   const int CV = C >> 3;
   const int b = blockIdx.y;
@@ -169,6 +173,8 @@ template <int LPR>
 __global__ void __launch_bounds__(256)
 layernorm40_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ gamma,
                    const float* __restrict__ beta, int rows, float eps) {
+  pdl_launch_dependents();  // programmatic dependent launch: the next kernel may start its prologue
+  pdl_wait();               // ... and this one touches global memory only after its predecessor finished
   constexpr int C = 40 * LPR;
   constexpr int CV = C / 8;  // 5 * LPR
   constexpr int RPW = 32 / LPR;
@@ -234,6 +240,8 @@ constexpr int LN_MAX_VEC = 5;  // generic path: C <= 1280
 __global__ void __launch_bounds__(256)
 layernorm_generic_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ gamma,
                          const float* __restrict__ beta, int rows, int C, float eps) {
+  pdl_launch_dependents();  // programmatic dependent launch: the next kernel may start its prologue
+  pdl_wait();               // ... and this one touches global memory only after its predecessor finished
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -328,11 +336,8 @@ extern "C" int idiff_groupnorm(const void* x, void* y, const float* gamma, const
   }
   IDIFF_REQUIRE(smem <= 96 * 1024, "idiff_groupnorm: shared memory %zu too large", smem);
   dim3 grid(chunks, batch);
-  gn_stats_kernel<<<grid, threads, smem, s>>>(reinterpret_cast<const uint4*>(x), stats_ws, hw, channels,
-                                              groups, ppb, k);
-  gn_apply_kernel<<<grid, threads, 0, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y),
-                                           gamma, beta, stats_ws, hw, channels, groups, eps, fuse_silu, ppb,
-                                           k, chunks);
+  IDIFF_CHECK_CUDA(launch_pdl(gn_stats_kernel, dim3(grid), dim3(threads), smem, s, reinterpret_cast<const uint4*>(x), stats_ws, hw, channels, groups, ppb, k));
+  IDIFF_CHECK_CUDA(launch_pdl(gn_apply_kernel, dim3(grid), dim3(threads), 0, s, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), gamma, beta, stats_ws, hw, channels, groups, eps, fuse_silu, ppb, k, chunks));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -356,13 +361,13 @@ extern "C" int idiff_layernorm(const void* x, void* y, const float* gamma, const
     return (rows + rpb - 1) / rpb;
   };
   if (channels == 320) {
-    layernorm40_kernel<8><<<blocks(4), 256, 0, s>>>(xi, yo, gamma, beta, rows, eps);
+    IDIFF_CHECK_CUDA(launch_pdl(layernorm40_kernel<8>, dim3(blocks(4)), dim3(256), 0, s, xi, yo, gamma, beta, rows, eps));
   } else if (channels == 640) {
-    layernorm40_kernel<16><<<blocks(2), 256, 0, s>>>(xi, yo, gamma, beta, rows, eps);
+    IDIFF_CHECK_CUDA(launch_pdl(layernorm40_kernel<16>, dim3(blocks(2)), dim3(256), 0, s, xi, yo, gamma, beta, rows, eps));
   } else if (channels == 1280) {
-    layernorm40_kernel<32><<<blocks(1), 256, 0, s>>>(xi, yo, gamma, beta, rows, eps);
+    IDIFF_CHECK_CUDA(launch_pdl(layernorm40_kernel<32>, dim3(blocks(1)), dim3(256), 0, s, xi, yo, gamma, beta, rows, eps));
   } else {
-    layernorm_generic_kernel<<<blocks(1), 256, 0, s>>>(xi, yo, gamma, beta, rows, channels, eps);
+    IDIFF_CHECK_CUDA(launch_pdl(layernorm_generic_kernel, dim3(blocks(1)), dim3(256), 0, s, xi, yo, gamma, beta, rows, channels, eps));
   }
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
