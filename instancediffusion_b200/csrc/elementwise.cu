@@ -7,7 +7,6 @@
 
 namespace idiff {
 
-constexpr float kTwoPi = 6.283185307179586f;
 
 // ---------------------------------------------------------------------------------------------
 // layout conversion
