@@ -67,8 +67,8 @@ int idiff_gemm(const idiff_gemm_args* args, void* stream);
  * not share it. */
 long idiff_gemm_workspace_bytes(void);
 int idiff_set_gemm_workspace(void* ptr, long bytes);
-/* Profiling hook: device buffer of 8 x uint64 per CTA (>= 148*8) receiving %globaltimer stamps of
- * each GEMM CTA's phases; NULL (default) disables it. */
+/* Profiling hook: device buffer of 16 x uint64 per CTA (>= 148*16) receiving %globaltimer stamps of
+ * each GEMM CTA's phases (tools/trace_gemm.py names them); NULL (default) disables it. */
 int idiff_set_gemm_trace(void* ptr);
 
 /* ---------------------------------------------------------------------------------------------

@@ -1055,9 +1055,9 @@ extern "C" int idiff_set_gemm_workspace(void* ptr, long bytes) {
   return 0;
 }
 
-// Debug / profiling hook: when set, every GEMM CTA writes 8 %globaltimer stamps (kernel entry,
-// first operand tile landed, first segment issued, first accumulator ready, fixup done, first
-// epilogue done, role loops done, exit) to trace[cta*8 ..].  Pass NULL to disable (default).
+// Debug / profiling hook: when set, every GEMM CTA writes %globaltimer stamps (kernel entry, first
+// operand tile landed, first segment issued, first accumulator ready, fixup done, first epilogue
+// done, role loops done, exit, then per-chunk epilogue phases) to trace[cta*16 ..].  NULL disables.
 extern "C" int idiff_set_gemm_trace(void* ptr) {
   idiff::v2::g_trace = reinterpret_cast<unsigned long long*>(ptr);
   return 0;
