@@ -166,6 +166,151 @@ gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Single-pass GroupNorm (opt-in, IDIFF_GN_FUSED=1; not yet the default).  One thread-block cluster per
+// (sample, slab of CS channels = whole groups): every CTA of the cluster streams its share of the
+// pixels once from global memory into shared memory while accumulating per-channel sums, the
+// per-group partial sums of the CL CTAs are exchanged through distributed shared memory and added in
+// rank order (deterministic), and the tile is normalised (+SiLU) straight from shared memory.
+// 4 B per element of global traffic and one launch instead of 6 B and two.
+// grid (CL * nslabs, B), cluster (CL, 1, 1), block k*CV with CV = CS/8.
+// dynamic smem: tile [rows][CV] uint4, then red [k][CS][2] floats.
+// ---------------------------------------------------------------------------------------------
+constexpr int GNF_MAX_SLAB_GROUPS = 8;
+
+IDIFF_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+IDIFF_DEVICE float ld_dsmem_f32(const float* local, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(smem_u32(local)), "r"(rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];\n" : "=f"(v) : "r"(raddr) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(512)
+gn_fused_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int hw, int C, int groups, float eps, int fuse_silu, int CS,
+                int CL, int k) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t gnf_smem[];
+  __shared__ float cta_part[GNF_MAX_SLAB_GROUPS * 2];  // this CTA's (sum, sumsq) per group of the slab
+  __shared__ float s_mean[GNF_MAX_SLAB_GROUPS], s_rstd[GNF_MAX_SLAB_GROUPS];
+  const int CV = CS >> 3;       // 16-byte vectors per pixel of the slab
+  const int CVT = C >> 3;       // ... of the whole tensor
+  const int rank = blockIdx.x % CL;
+  const int slab = blockIdx.x / CL;
+  const int b = blockIdx.y;
+  const int rows = hw / CL;     // pixels of this CTA (host guarantees divisibility)
+  const int cpg = C / groups;
+  const int ng = CS / cpg;      // groups in the slab
+  uint4* tile = reinterpret_cast<uint4*>(gnf_smem);
+  float* red = reinterpret_cast<float*>(gnf_smem + (size_t)rows * CV * sizeof(uint4));
+
+  const int r = threadIdx.x / CV;
+  const int cv = threadIdx.x - r * CV;
+  const uint4* xb = x + ((long)b * hw + (long)rank * rows) * CVT + slab * CV + cv;
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  int pix = r;
+  for (; pix + 3 * k < rows; pix += 4 * k) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = xb[(long)(pix + u * k) * CVT];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      tile[(pix + u * k) * CV + cv] = v[u];
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        ss[j] += f[j] * f[j];
+      }
+    }
+  }
+  for (; pix < rows; pix += k) {
+    const uint4 v = xb[(long)pix * CVT];
+    tile[pix * CV + cv] = v;
+    float f[8];
+    unpack8(v, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += f[j];
+      ss[j] += f[j] * f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[((r * CS) + cv * 8 + j) * 2] = s[j];
+    red[((r * CS) + cv * 8 + j) * 2 + 1] = ss[j];
+  }
+  __syncthreads();
+  // one warp per group of the slab (round robin), fixed summation order
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int g = warp; g < ng; g += nwarps) {
+    float a = 0.f, q = 0.f;
+    for (int i = lane; i < cpg * k; i += 32) {
+      const int rr = i / cpg, c = g * cpg + (i - rr * cpg);
+      a += red[(rr * CS + c) * 2];
+      q += red[(rr * CS + c) * 2 + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+      cta_part[g * 2] = a;
+      cta_part[g * 2 + 1] = q;
+    }
+  }
+  cluster_sync_all();  // every CTA's partials are written and visible cluster-wide
+  if (threadIdx.x < ng) {
+    float a = 0.f, q = 0.f;
+    for (int rk = 0; rk < CL; ++rk) {  // rank order: the same sum in every CTA of the cluster
+      a += ld_dsmem_f32(&cta_part[threadIdx.x * 2], rk);
+      q += ld_dsmem_f32(&cta_part[threadIdx.x * 2 + 1], rk);
+    }
+    const float inv_n = 1.0f / (float)((long)cpg * hw);
+    const float mean = a * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rsqrtf(var + eps);
+  }
+  cluster_sync_all();  // (also a CTA barrier) no CTA leaves while its partials may still be read
+  float sa[8], sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int cl = cv * 8 + j;          // channel within the slab
+    const int c = slab * CS + cl;       // channel of the tensor
+    const float a = s_rstd[cl / cpg] * gamma[c];
+    sa[j] = a;
+    sb[j] = beta[c] - s_mean[cl / cpg] * a;
+  }
+  uint4* yb = y + ((long)b * hw + (long)rank * rows) * CVT + slab * CV + cv;
+  for (pix = r; pix < rows; pix += k) {
+    float f[8];
+    unpack8(tile[pix * CV + cv], f);  // written by this very thread above
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float r0 = f[2 * j] * sa[2 * j] + sb[2 * j];
+      float r1 = f[2 * j + 1] * sa[2 * j + 1] + sb[2 * j + 1];
+      if (fuse_silu) {
+        r0 = silu_f(r0);
+        r1 = silu_f(r1);
+      }
+      o[j] = pack_half2(r0, r1);
+    }
+    yb[(long)pix * CVT] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // LayerNorm.  Fast path: C in {320, 640, 1280} = 40 * LPR: LPR lanes cooperate on a row, five
 // 16-byte vectors per lane held in registers, 32/LPR rows per warp.  Generic path: one warp per row.
 // ---------------------------------------------------------------------------------------------
@@ -316,6 +461,33 @@ static void gn_geometry(int batch, int hw, int channels, int* k, int* ppb, int* 
   *chunks = (hw + p - 1) / p;
 }
 
+// Single-pass variant: slab width CS (whole groups and whole 16-byte vectors), cluster size CL (pixels
+// split over CL CTAs), k pixel rows per block pass.  Returns false when the shape does not fit.
+static bool gn_fused_geometry(int batch, int hw, int channels, int groups, int* CS, int* CL, int* k, size_t* smem) {
+  const int cpg = channels / groups;
+  int unit = cpg;  // lcm(cpg, 8)
+  while (unit % 8 != 0) unit += cpg;
+  if (channels % unit != 0 || unit / cpg > idiff::GNF_MAX_SLAB_GROUPS) return false;
+  int cs = unit;
+  while (cs * 2 <= 160 && channels % (cs * 2) == 0 && (cs * 2) / cpg <= idiff::GNF_MAX_SLAB_GROUPS) cs *= 2;
+  const int CV = cs / 8;
+  int kk = 512 / CV;
+  if (kk < 1) return false;
+  int cl = 1;
+  const size_t budget = 160 * 1024;
+  while (cl < 8 && ((size_t)(hw / cl) * cs * 2 > budget)) cl *= 2;
+  if (hw % cl != 0 || (size_t)(hw / cl) * cs * 2 > budget) return false;
+  // fill the machine: more CTAs per sample while the launch is below one wave
+  while (cl < 8 && hw % (cl * 2) == 0 && (long)batch * (channels / cs) * cl < 128 && hw / (cl * 2) >= kk) cl *= 2;
+  if (kk > hw / cl) kk = hw / cl;
+  if (kk < 1) return false;
+  *CS = cs;
+  *CL = cl;
+  *k = kk;
+  *smem = (size_t)(hw / cl) * cs * 2 + (size_t)kk * cs * 2 * sizeof(float);
+  return *smem <= 200 * 1024;
+}
+
 extern "C" int idiff_groupnorm(const void* x, void* y, const float* gamma, const float* beta,
                                float* stats_ws, int batch, int hw, int channels, int groups,
                                float eps, int fuse_silu, void* stream) {
@@ -325,6 +497,35 @@ extern "C" int idiff_groupnorm(const void* x, void* y, const float* gamma, const
                 "idiff_groupnorm: bad groups=%d for C=%d", groups, channels);
   IDIFF_REQUIRE(channels % 8 == 0 && channels <= 4096, "idiff_groupnorm: C=%d must be a multiple of 8, <= 4096", channels);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  {
+    const char* fe = getenv("IDIFF_GN_FUSED");  // read per call so tests can cover both paths
+    const bool fused_on = fe && fe[0] == '1';
+    int CS, CL, kf;
+    size_t smem_f;
+    if (fused_on && gn_fused_geometry(batch, hw, channels, groups, &CS, &CL, &kf, &smem_f)) {
+      static bool fattr = false;
+      if (!fattr) {
+        IDIFF_CHECK_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        fattr = true;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(CL * (channels / CS), batch);
+      cfg.blockDim = dim3(kf * (CS / 8));
+      cfg.dynamicSmemBytes = smem_f;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = CL;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      IDIFF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel, reinterpret_cast<const uint4*>(x),
+                                          reinterpret_cast<uint4*>(y), gamma, beta, hw, channels, groups, eps,
+                                          fuse_silu, CS, CL, kf));
+      return 0;
+    }
+  }
   int k, ppb, chunks;
   gn_geometry(batch, hw, channels, &k, &ppb, &chunks);
   const int threads = k * (channels / 8);

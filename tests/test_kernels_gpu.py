@@ -272,6 +272,31 @@ def test_groupnorm(cuda_device, B, HW, C, silu, eps):
     _check(out, ref, 2e-3, 2e-3, f"groupnorm B{B} HW{HW} C{C}")
 
 
+@pytest.mark.parametrize("B,HW,C", [(8, 4096, 320), (8, 4096, 640), (8, 4096, 960), (8, 1024, 640), (8, 1024, 1280),
+                                    (8, 1024, 1920), (8, 1024, 960), (8, 256, 1280), (8, 256, 2560), (8, 256, 1920),
+                                    (8, 64, 1280), (8, 64, 2560), (2, 4096, 320), (1, 256, 1280)])
+def test_groupnorm_single_pass(cuda_device, B, HW, C):
+    """The opt-in cluster kernel (IDIFF_GN_FUSED=1: one pass, statistics exchanged through distributed
+    shared memory) at every GroupNorm shape of the UNet; it must agree with torch and, to fp32
+    summation-order noise, with the two-kernel default."""
+    ops = _ops()
+    x = (_randn((B * HW, C), cuda_device, 1.5, 1) + 0.3).half()
+    gamma = 1.0 + _randn((C,), cuda_device, 0.2, 2)
+    beta = _randn((C,), cuda_device, 0.2, 3)
+    base = ops.groupnorm(x, gamma, beta, batch=B, hw=HW, groups=32, eps=1e-5, silu=True)
+    os.environ["IDIFF_GN_FUSED"] = "1"
+    try:
+        out = ops.groupnorm(x, gamma, beta, batch=B, hw=HW, groups=32, eps=1e-5, silu=True)
+        again = ops.groupnorm(x, gamma, beta, batch=B, hw=HW, groups=32, eps=1e-5, silu=True)
+    finally:
+        os.environ.pop("IDIFF_GN_FUSED", None)
+    ref = F.silu(F.group_norm(x.float().view(B, HW, C).permute(0, 2, 1), 32, gamma, beta, 1e-5))
+    ref = ref.permute(0, 2, 1).reshape(B * HW, C)
+    _check(out, ref, 2e-3, 2e-3, f"single-pass groupnorm B{B} HW{HW} C{C}")
+    _check(out, base.float(), 2e-3, 2e-3, f"single-pass vs two-kernel groupnorm B{B} HW{HW} C{C}")
+    assert torch.equal(out, again), "single-pass groupnorm is not deterministic"
+
+
 @pytest.mark.parametrize("rows,C", [(4096, 320), (1000, 640), (77, 1280)])
 def test_layernorm(cuda_device, rows, C):
     ops = _ops()
