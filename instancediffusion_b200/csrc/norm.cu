@@ -485,6 +485,9 @@ static bool gn_fused_geometry(int batch, int hw, int channels, int groups, int* 
   *CL = cl;
   *k = kk;
   *smem = (size_t)(hw / cl) * cs * 2 + (size_t)kk * cs * 2 * sizeof(float);
+  // Measured (profiles/README.md, NEXT.md): with these 100-190 KB tiles the single pass wins only while
+  // the whole launch is resident at once; beyond one wave the two-kernel path is faster.
+  if ((long)batch * (channels / cs) * cl > 148) return false;
   return *smem <= 200 * 1024;
 }
 
