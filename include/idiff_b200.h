@@ -43,6 +43,7 @@ int idiff_version(void);
                                    (value+b)*gelu_erf(gate+b)            (attention.py:41-43)   */
 #define IDIFF_EPI_SILU 2        /* x -> x*sigmoid(x) after bias                                   */
 #define IDIFF_OUT_F32_NCHW 4    /* out is fp32 (B, N, H*W): the eps layout the samplers consume   */
+#define IDIFF_EPI_GELU 8        /* x -> exact (erf) GELU after bias: ConvNeXt pwconv1 (convnext.py:31,42) */
 
 typedef struct {
   const void* a;        /* fp16 [M, K] (lda)            | conv: fp16 NHWC activation            */
@@ -58,13 +59,18 @@ typedef struct {
   int rows_per_batch;
   int flags;
   int conv_b, conv_h, conv_w, conv_cin;
+  void* workspace;      /* optional stream-K scratch of this call (>= idiff_gemm_workspace_bytes(), 256B aligned,
+                           zero-initialised once by the caller, then owned by the library between calls on ONE
+                           stream); NULL = the process-wide default of idiff_set_gemm_workspace, if any        */
+  long workspace_bytes;
 } idiff_gemm_args;
 int idiff_gemm(const idiff_gemm_args* args, void* stream);
-/* Optional stream-K scratch (fp32 partial tiles + flags) for load-balancing GEMMs whose tile count
- * is not a multiple of the SM count.  Caller-owned device memory of at least
- * idiff_gemm_workspace_bytes(); zeroed by the call (synchronous).  Without it every GEMM runs
- * data-parallel.  One workspace per process / stream: concurrent GEMMs on different streams must
- * not share it. */
+/* Stream-K scratch (fp32 partial tiles + flags) for load-balancing GEMMs whose tile count is not a
+ * multiple of the SM count.  Caller-owned device memory of at least idiff_gemm_workspace_bytes().
+ * Preferred: pass it per call in idiff_gemm_args.workspace (one buffer per stream -- GEMMs in flight on
+ * different streams must not share flags).  idiff_set_gemm_workspace registers a process-wide default
+ * for callers that use a single stream (zeroed by the call, synchronous).  Without any scratch every
+ * GEMM runs data-parallel. */
 long idiff_gemm_workspace_bytes(void);
 int idiff_set_gemm_workspace(void* ptr, long bytes);
 /* Profiling hook: device buffer of 16 x uint64 per CTA (>= 148*16) receiving %globaltimer stamps of
@@ -168,6 +174,27 @@ int idiff_latent_mean(const float* const* xs_dev, int count, float* out, long n,
 /* timestep_embedding (util.py:160-180): out fp16 [B, dim] = [cos(t*f) | sin(t*f)],
    f_k = exp(-ln(1e4)*k/(dim/2)) */
 int idiff_timestep_embedding(const float* t, void* out, int batch, int dim, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ConvNeXt mask encoder of UniFusion (mask conditioning; runs once per sample).  The pointwise and
+ * strided convolutions are idiff_gemm calls (IDIFF_EPI_GELU for pwconv1); these are the other pieces.
+ * ------------------------------------------------------------------------------------------- */
+/* text_grounding_net.py:227-228: y = Conv2d(cin,3,3,1,1)(F.interpolate(segs, out_size, "nearest")) as
+   NHWC fp16 (B, out_size, out_size, 3); seg_sum[b] = sum of the resized masks (the `> 0` test of :279).
+   segs: fp32 (B, cin, in_size, in_size) with element strides `strides[4]` (host array; expanded / zero
+   strides allowed); w: fp32 [3][cin][3][3]; bias fp32 [3]. */
+int idiff_segs_inconv(const float* segs, const long* strides, const float* w, const float* bias, void* y,
+                      float* seg_sum, int batch, int cin, int in_size, int out_size, void* stream);
+/* NHWC fp16 (B,H,W,C) -> rows [B*(H/p)*(W/p), p*p*C], column (ky*p+kx)*C + c: the operand of the kernel-p,
+   stride-p convolutions (convnext.py:71-81) run as GEMMs */
+int idiff_patchify(const void* x, void* y, int batch, int h, int w, int c, int p, void* stream);
+/* depthwise 7x7, padding 3 (convnext.py:28) on NHWC fp16; w fp32 [49][C] (tap-major), bias fp32 [C] */
+int idiff_dwconv7x7(const void* x, const float* w, const float* bias, void* y, int batch, int h, int w_, int c,
+                    void* stream);
+/* text_grounding_net.py:229-230,277-285: out[b*T+t, r] = seg_sum[b] > 0 ? feat_nchw_flat[b][r*T+t] + pos[t,r]
+   : null_pos[t,r], feat given as NHWC fp16 [B, P, C]; F = C*P/T features per token */
+int idiff_seg_tokens(const void* feat, const void* null_pos, const float* pos, const float* seg_sum, void* out,
+                     int batch, int pixels, int channels, int tokens, void* stream);
 
 /* y = x * sigmoid(x) on fp16 (the nn.SiLU in front of ResBlock.emb_layers, openaimodel.py:200, when
    a ResBlock is driven through its module-level forward; the UNet path fuses it into a GEMM epilogue) */

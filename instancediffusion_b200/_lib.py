@@ -24,6 +24,7 @@ class GemmArgs(C.Structure):
         ("lda", C.c_int), ("ldw", C.c_int), ("ldo", C.c_int), ("ldr", C.c_int), ("ldra", C.c_int),
         ("rows_per_batch", C.c_int), ("flags", C.c_int),
         ("conv_b", C.c_int), ("conv_h", C.c_int), ("conv_w", C.c_int), ("conv_cin", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_long),
     ]
 
 
@@ -42,6 +43,7 @@ class AttnArgs(C.Structure):
 EPI_GEGLU = 1
 EPI_SILU = 2
 OUT_F32_NCHW = 4
+EPI_GELU = 8
 
 # name -> (restype, argtypes); the exported surface of include/idiff_b200.h
 _vp, _i, _f, _l = C.c_void_p, C.c_int, C.c_float, C.c_long
@@ -67,6 +69,10 @@ SIGNATURES = {
     "idiff_latent_mean": (_i, [_vp, _i, _vp, _l, _vp]),
     "idiff_timestep_embedding": (_i, [_vp, _vp, _i, _i, _vp]),
     "idiff_silu_f16": (_i, [_vp, _vp, _l, _vp]),
+    "idiff_segs_inconv": (_i, [_vp, C.POINTER(C.c_long), _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "idiff_patchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "idiff_dwconv7x7": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "idiff_seg_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

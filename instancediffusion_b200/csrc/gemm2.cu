@@ -2,8 +2,10 @@
 //
 //   out[M, N] = epilogue( A[M, K] . W[N, K]^T )        fp16 operands, fp32 accumulation in TMEM
 //
-// Differences to the first kernel (gemm.cu), driven by the measured shape mix of the UNet
-// (profiles/r1_v0_launches_forward_b8.csv):
+// Replaces (reference file:line): attention.py:41,62,121-125,175-179,297,354,363;
+// openaimodel.py:109,134,186,205,213,361-363,464; text_grounding_net.py:75-81; convnext.py:30-32,71-81.
+// Design points, driven by the measured shape mix of the UNet (profiles/r1_v0_launches_forward_b8.csv;
+// the round-1 one-tile-per-CTA kernel this replaced is in the git history, not in the tree):
 //   * one persistent CTA per SM; work = (128 x BN tile, k-block range) segments.  Full waves of
 //     tiles are processed data-parallel; the ragged last 1-2 waves are split evenly over all CTAs
 //     in units of 64-wide k-blocks ("stream-K"), so 40-, 160- and 320-tile problems no longer leave
@@ -21,11 +23,13 @@
 //     registers before the accumulator is ready.  One kernel per (BN, epilogue mode, TMA epilogue).
 // Warp roles (384 threads = 3 warpgroups): warp 0 TMA producer, warp 1 TMEM allocator + UMMA
 // issuer (warps 2-3 idle; the group gives registers back with setmaxnreg), warps 4..11 epilogue.
-// conv3x3 gathers the A tile tap by tap with a 4-D TMA box (zero fill at the borders), exactly as
-// in gemm.cu.
+// conv3x3 gathers the A tile tap by tap with a 4-D TMA box over the NHWC activation; out-of-image taps
+// are zero-filled by the TMA unit (no im2col buffer, no halo copy).
 #include "../../include/idiff_b200.h"
 #include "common.cuh"
 #include "host.cuh"
+
+#include <stdlib.h>
 
 namespace idiff {
 namespace v2 {
@@ -302,6 +306,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     constexpr bool geglu = (MODE == MODE_GEGLU);
     constexpr bool nchw = (MODE == MODE_NCHW);
     const bool do_silu = (p.flags & IDIFF_EPI_SILU) != 0;
+    const bool do_gelu = (p.flags & IDIFF_EPI_GELU) != 0;
     const int n_out_total = geglu ? p.N / 2 : p.N;
     constexpr int NCH = BN / 2 / CHUNK;  // accumulator chunks owned by this warp
     // Accumulator column of chunk `ch` of this warp.  Plain: a contiguous half of the tile.
@@ -584,6 +589,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               if (do_silu) {
 #pragma unroll
                 for (int j = 0; j < CHUNK; ++j) x[j] = silu_f(x[j]);
+              } else if (do_gelu) {
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j) x[j] = gelu_erf_f(x[j]);
               }
             }
             // box `ch`: row `lane` is 32 B; SWIZZLE_32B puts 16-byte chunk q at (q ^ ((lane >> 2) & 1)).
@@ -687,6 +695,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               if (do_silu) {
 #pragma unroll
                 for (int j = 0; j < CHUNK; ++j) x[j] = silu_f(x[j]);
+              } else if (do_gelu) {
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j) x[j] = gelu_erf_f(x[j]);
               }
             }
 #pragma unroll
@@ -896,15 +907,19 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream, bool want_sk) {
   // Stream-K needs the fixup workspace (flags in its first 64 KiB, partial tiles after); short-K
   // problems (fixup cost ~ mainloop) and exact multiples of the SM count stay data-parallel.
   const long ws_need = kFlagBytes + (long)g_num_sms * 128 * BN * sizeof(float);
-  const bool use_sk = want_sk && g_ws && g_ws_bytes >= ws_need && p.KB >= 8 && (p.T % g_num_sms) != 0 &&
+  // per-call scratch (idiff_gemm_args.workspace: one per stream, so concurrent streams never share flags)
+  // takes precedence over the process-wide default of idiff_set_gemm_workspace
+  void* ws_ptr = a->workspace ? a->workspace : g_ws;
+  const long ws_bytes = a->workspace ? a->workspace_bytes : g_ws_bytes;
+  const bool use_sk = want_sk && ws_ptr && ws_bytes >= ws_need && p.KB >= 8 && (p.T % g_num_sms) != 0 &&
                       (long)p.T * p.KB >= g_num_sms;
   if (use_sk) {
     p.G = g_num_sms;
     const int waves = p.T / p.G;
     p.T_dp = (waves >= 2) ? (waves - 1) * p.G : 0;
     p.U_sk = (long)(p.T - p.T_dp) * p.KB;
-    p.sflags = reinterpret_cast<int*>(g_ws);
-    p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_ws) + kFlagBytes);
+    p.sflags = reinterpret_cast<int*>(ws_ptr);
+    p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws_ptr) + kFlagBytes);
   } else {
     p.G = g_num_sms < p.T ? g_num_sms : p.T;
     p.T_dp = p.T;
@@ -1042,6 +1057,33 @@ int gemm_v2(const idiff_gemm_args* a, cudaStream_t stream) {
 
 }  // namespace v2
 }  // namespace idiff
+
+extern "C" int idiff_gemm(const idiff_gemm_args* a, void* stream) {
+  using namespace idiff;
+  IDIFF_REQUIRE(a && a->a && a->w && a->out, "idiff_gemm: null pointer argument");
+  IDIFF_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "idiff_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  const bool geglu = (a->flags & IDIFF_EPI_GEGLU) != 0;
+  const bool nchw = (a->flags & IDIFF_OUT_F32_NCHW) != 0;
+  if (geglu) {
+    IDIFF_REQUIRE(a->N % 256 == 0, "idiff_gemm: GEGLU needs N %% 256 == 0 (N=%d)", a->N);
+    IDIFF_REQUIRE(!a->residual && !a->rowadd && !nchw, "idiff_gemm: GEGLU excludes residual/rowadd/NCHW");
+  }
+  if (!nchw) {
+    IDIFF_REQUIRE(a->N % 8 == 0, "idiff_gemm: N=%d must be a multiple of 8 for fp16 output", a->N);
+    IDIFF_REQUIRE(a->ldo % 8 == 0, "idiff_gemm: ldo=%d must be a multiple of 8", a->ldo);
+    IDIFF_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "idiff_gemm: out not 16B aligned");
+    if (a->residual) {
+      IDIFF_REQUIRE(a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0,
+                    "idiff_gemm: residual must be 16B aligned with ldr %% 8 == 0");
+    }
+  } else {
+    IDIFF_REQUIRE(!a->residual, "idiff_gemm: NCHW fp32 output excludes residual");
+  }
+  if (a->workspace) {
+    IDIFF_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "idiff_gemm: workspace must be 256B aligned");
+  }
+  return v2::gemm_v2(a, reinterpret_cast<cudaStream_t>(stream));
+}
 
 extern "C" int idiff_set_gemm_workspace(void* ptr, long bytes) {
   using namespace idiff;

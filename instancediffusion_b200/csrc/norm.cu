@@ -76,10 +76,29 @@ gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int hw
     red[((r * C) + cv * 8 + j) * 2 + 1] = ss[j];
   }
   __syncthreads();
-  // one warp per group (round robin), fixed summation order
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // one FULL warp per group (round robin), fixed summation order.  blockDim = k*CV is generally not a
+  // multiple of 32 (e.g. 240 for C=320): the trailing partial warp must not take part -- it would
+  // shuffle with absent lanes and write the same `partial` slots as a full warp.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nfull = blockDim.x >> 5;
   const int cpg = C / groups;
-  for (int g = warp; g < groups; g += nwarps) {
+  if (nfull == 0) {  // fewer than 32 threads (tiny maps through the C ABI): serial, still fixed order
+    if (threadIdx.x == 0) {
+      for (int g = 0; g < groups; ++g) {
+        float a = 0.f, q = 0.f;
+        for (int i = 0; i < cpg * k; ++i) {
+          const int rr = i / cpg, c = g * cpg + (i - rr * cpg);
+          a += red[(rr * C + c) * 2];
+          q += red[(rr * C + c) * 2 + 1];
+        }
+        float* dst = partial + (((long)b * gridDim.x + blockIdx.x) * groups + g) * 2;
+        dst[0] = a;
+        dst[1] = q;
+      }
+    }
+    return;
+  }
+  if (warp >= nfull) return;
+  for (int g = warp; g < groups; g += nfull) {
     float a = 0.f, q = 0.f;
     for (int i = lane; i < cpg * k; i += 32) {
       const int rr = i / cpg, c = g * cpg + (i - rr * cpg);
@@ -110,18 +129,18 @@ gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float*
   const int CV = C >> 3;
   const int b = blockIdx.y;
   const int cpg = C / groups;
-  if (threadIdx.x < groups) {
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {  // blockDim may be < groups on tiny maps
     float a = 0.f, q = 0.f;
     for (int ch = 0; ch < stat_chunks; ++ch) {
-      const float* src = partial + (((long)b * stat_chunks + ch) * groups + threadIdx.x) * 2;
+      const float* src = partial + (((long)b * stat_chunks + ch) * groups + g) * 2;
       a += src[0];
       q += src[1];
     }
     const float inv_n = 1.0f / (float)((long)cpg * hw);
     const float mean = a * inv_n;
     const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-    s_mean[threadIdx.x] = mean;
-    s_rstd[threadIdx.x] = rsqrtf(var + eps);
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(var + eps);
   }
   __syncthreads();
   const int r = threadIdx.x / CV;
@@ -250,8 +269,9 @@ gn_fused_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float*
   }
   __syncthreads();
   // one warp per group of the slab (round robin), fixed summation order
+  // full warps only (blockDim = k*CV need not be a multiple of 32; gn_fused_geometry guarantees >= 32)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int g = warp; g < ng; g += nwarps) {
+  for (int g = warp; warp < nwarps && g < ng; g += nwarps) {
     float a = 0.f, q = 0.f;
     for (int i = lane; i < cpg * k; i += 32) {
       const int rr = i / cpg, c = g * cpg + (i - rr * cpg);
@@ -480,7 +500,7 @@ static bool gn_fused_geometry(int batch, int hw, int channels, int groups, int* 
   // fill the machine: more CTAs per sample while the launch is below one wave
   while (cl < 8 && hw % (cl * 2) == 0 && (long)batch * (channels / cs) * cl < 128 && hw / (cl * 2) >= kk) cl *= 2;
   if (kk > hw / cl) kk = hw / cl;
-  if (kk < 1) return false;
+  if (kk < 1 || kk * CV < 32) return false;  // the group reduction needs at least one full warp
   *CS = cs;
   *CL = cl;
   *k = kk;

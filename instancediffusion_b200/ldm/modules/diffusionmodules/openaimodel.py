@@ -377,17 +377,26 @@ class UNetModel(PackedModule):
             self._in_packs[key] = hit
         return hit
 
-    def _apply(self, fn, *a, **k):
+    def _drop_derived(self):
+        """Everything computed from the weights: packed first conv, captured graphs, hoisted text K/V and
+        object tokens / per-fuser K/V (including the null-branch entry)."""
         if hasattr(self, "_in_packs"):
             self._in_packs.clear()
             self._graphs.clear()
+            self._ctx_cache.clear()
+            self._obj_cache.clear()
+
+    def _apply(self, fn, *a, **k):
+        self._drop_derived()
         return super()._apply(fn, *a, **k)
 
     def _load_from_state_dict(self, *a, **k):
-        if hasattr(self, "_in_packs"):
-            self._in_packs.clear()
-            self._graphs.clear()
+        self._drop_derived()
         return super()._load_from_state_dict(*a, **k)
+
+    def invalidate_pack(self):
+        self._drop_derived()
+        return super().invalidate_pack()
 
     # ------------------------------------------------------------------------------------------
     # packing
@@ -426,6 +435,8 @@ class UNetModel(PackedModule):
         # ScaleU factors (openaimodel.py:524-525): tanh(b)+1 per channel, tanh(s)+1 scalar
         p["scaleu_b"] = [(torch.tanh(getattr(self, f"scaleu_b_{i}").detach().float()) + 1).contiguous()
                          for i in range(len(self.output_blocks))]
+        p["ones"] = torch.ones(max(getattr(self, f"scaleu_b_{i}").numel() for i in range(len(self.output_blocks))),
+                               dtype=torch.float32, device=p["g_out"].device)
         p["scaleu_s"] = [float(torch.tanh(getattr(self, f"scaleu_s_{i}").detach().float().cpu()) + 1)
                          for i in range(len(self.output_blocks))]
         return p
@@ -455,8 +466,11 @@ class UNetModel(PackedModule):
         """UniFusion tokens -> per-fuser K|V ([Bo*184, 2C] each), cached per grounding_input dict.
         `None` selects the null (CFG-uncond) tokens, which are a pure function of the weights."""
         if grounding_input is None:
-            key = ("null",)
-            gi = self.grounding_tokenizer_input.get_null_input()
+            gti = self.grounding_tokenizer_input
+            gi = gti.get_null_input()
+            # the null tokens depend on the weights and on the shapes prepare() remembered
+            key = ("null", gti.batch, gti.max_box, gti.in_dim, gti.dim_scribbles, gti.dim_polygons,
+                   str(gi["boxes"].device))
         else:
             gi = grounding_input
             key = tuple(self._tkey(gi[k]) for k in ("boxes", "masks", "positive_embeddings", "scribbles",
@@ -539,7 +553,14 @@ class UNetModel(PackedModule):
         for idx, module in enumerate(self.output_blocks):
             skip, sh, sw = hs.pop()
             assert (sh, sw) == (hh, ww)
-            h = ops.scaleu_concat(h, skip, p["scaleu_b"][idx], p["scaleu_s"][idx], batch=B, height=hh, width=ww)
+            if self.enable_freeu or self.enable_se_scaleu:
+                raise NotImplementedError("FreeU / SE-ScaleU skip rescaling (openaimodel.py:519-560) is not on "
+                                          "the shipped sampling path; only enable_scaleu is implemented")
+            if self.enable_scaleu:
+                b1, s_ = p["scaleu_b"][idx], p["scaleu_s"][idx]
+            else:  # plain torch.cat([h, hs.pop()], dim=1): unit factors make the pass an exact copy
+                b1, s_ = p["ones"][: h.shape[-1]], 1.0
+            h = ops.scaleu_concat(h, skip, b1, s_, batch=B, height=hh, width=ww)
             h, hh, ww = run_block(module, h, hh, ww)
         h = ops.groupnorm(h, p["g_out"], p["b_out"], batch=B, hw=hh * ww, groups=32, eps=1e-5, silu=True)
         eps = torch.empty((B, self.out_channels, hh, ww), dtype=torch.float32, device=x.device)
@@ -559,7 +580,11 @@ class UNetModel(PackedModule):
                       else inp["timesteps"].float())
             ctxs.append(self.context_kv(inp["context"]))
             if active:
-                kvs, Bo, n_obj = self.object_kv(inp.get("grounding_input"))
+                kvs, Bo, n_obj_i = self.object_kv(inp.get("grounding_input"))
+                if n_obj and n_obj_i != n_obj:
+                    raise ValueError(f"inputs of one batched forward carry different object-token counts "
+                                     f"({n_obj} vs {n_obj_i}); prepare() them with the same max_box")
+                n_obj = n_obj_i
                 if Bo != b:
                     if Bo != 1:
                         raise ValueError(f"grounding batch {Bo} does not match latent batch {b}")
@@ -585,7 +610,12 @@ class UNetModel(PackedModule):
     def _run_core(self, x, t, ctx, M, okv, n_obj):
         if not self.use_cuda_graph:
             return self._core(x, t, ctx, M, okv, n_obj)
-        key = (tuple(x.shape), M, okv is not None, n_obj, getattr(self, "_first_conv_restored", False))
+        # the fuser gates scale*tanh(alpha) are kernel arguments, frozen into a captured graph: the
+        # per-fuser scales (set_alpha_scale may set any value, alpha_generator's decay stage is
+        # fractional) are part of the key
+        scales = tuple(float(blk.fuser.scale) for st in self._transformers() for blk in st.transformer_blocks) \
+            if okv is not None else ()
+        key = (tuple(x.shape), M, scales, n_obj, getattr(self, "_first_conv_restored", False))
         g = self._graphs.get(key)
         if g is None:
             g = _CoreGraph(self, x, t, ctx, M, okv, n_obj)
@@ -619,14 +649,15 @@ class _CoreGraph:
             if isinstance(m, PackedModule) and m is not model.position_net:
                 m.pk()
         # warm-up on a side stream (first-call attribute setup etc.), then capture
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            model._core(self.x, self.t, self.ctx, M, self.okv, n_obj)
-        torch.cuda.current_stream().wait_stream(s)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = model._core(self.x, self.t, self.ctx, M, self.okv, n_obj)
+        with ops.capture_workspace(self.x.device):  # stream-K scratch of captured GEMMs, allocated up front
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                model._core(self.x, self.t, self.ctx, M, self.okv, n_obj)
+            torch.cuda.current_stream().wait_stream(s)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = model._core(self.x, self.t, self.ctx, M, self.okv, n_obj)
 
     def replay(self, x, t, ctx, okv):
         self.x.copy_(x)

@@ -84,7 +84,20 @@ class UniFusion(PackedModule):
         p["null_polygon"] = f32(self.null_polygon_feature)
         # null seg tokens (segs all zero / dropped): null_seg + pos_embedding (:279-285), 64 rows
         p["seg_null_in"] = (f32(self.null_seg_feature)[None, :] + f32(self.pos_embedding)[0]).to(HALF).contiguous()
+        p["pos"] = f32(self.pos_embedding)[0].contiguous()
+        p["w_inconv"] = f32(self.in_conv.weight)
+        p["b_inconv"] = f32(self.in_conv.bias)
         return p
+
+    @staticmethod
+    def _all_planes_empty(segs: torch.Tensor) -> bool:
+        """Cheap exact shortcut for the spatially-constant `segs` the null / box-only inputs carry
+        (GroundingNetInput.get_null_input and synthetic.make_grounding_batch hand back a (B, N, 1, 1) tensor
+        expanded over the spatial dims): with stride-0 planes, sum(segs[b]) > 0 iff sum_n segs[b, n, 0, 0] > 0,
+        a B x N reduction.  Dense masks are never inspected on the host -- the kernels decide per sample."""
+        if segs.dim() != 4 or segs.stride(-1) != 0 or segs.stride(-2) != 0:
+            return False
+        return not bool((segs[:, :, 0, 0].float().sum(dim=1) > 0).any())
 
     def _mlp(self, idx, x16):
         (w0, b0), (w1, b1), (w2, b2) = self.pk()["mlp"][idx]
@@ -124,16 +137,22 @@ class UniFusion(PackedModule):
             ops.fourier_embed(coords, m, null_pos, buf, text=text, null_text=p["null_text"], mask_mode=mode,
                               dropped=dropped)
             toks.append(self._mlp(idx, buf).view(B, N, self.out_dim))
-        # mask tokens
-        has_seg = None
-        if not drop_segs and segs is not None:
-            has_seg = (torch.sum(segs, dim=(1, 2, 3)) > 0)
-            if bool(has_seg.any()):
-                raise NotImplementedError(
-                    "UniFusion: non-zero `segs` need the ConvNeXt mask encoder, which is not implemented yet "
-                    "(SURVEY.md section 8f); use box / point / scribble conditioning")
-        seg_tok = self._mlp(4, p["seg_null_in"])  # [64, out_dim], identical for every sample
-        toks.append(seg_tok.view(1, self.num_tokens, self.out_dim).expand(B, self.num_tokens, self.out_dim))
+        # mask tokens (text_grounding_net.py:226-231, 277-287): ConvNeXt features of the resized binary masks,
+        # reinterpreted as 64 tokens of 3072 features; samples whose masks sum to zero (and the dropped /
+        # CFG-null case) take the learned null feature -- decided per sample on the device from the sum the
+        # in_conv kernel accumulates.
+        if not drop_segs and segs is not None and not self._all_planes_empty(segs):
+            segs = segs.to(device=dev, dtype=torch.float32)
+            y, seg_sum = ops.segs_inconv(segs, p["w_inconv"], p["b_inconv"], self.resize_input)
+            feat, fh, fw = self.convnext_tiny_backbone._features(y, B, self.resize_input, self.resize_input)
+            if fh * fw * feat.shape[-1] != self.num_tokens * self.convnext_feature_dim:
+                raise ValueError("UniFusion: ConvNeXt feature map does not match num_tokens x convnext_feature_dim")
+            seg_in = ops.seg_tokens(feat, p["seg_null_in"], p["pos"], seg_sum, B, fh * fw, self.num_tokens)
+            seg_tok = self._mlp(4, seg_in).view(B, self.num_tokens, self.out_dim)
+        else:
+            seg_tok = self._mlp(4, p["seg_null_in"])  # [64, out_dim], identical for every sample
+            seg_tok = seg_tok.view(1, self.num_tokens, self.out_dim).expand(B, self.num_tokens, self.out_dim)
+        toks.append(seg_tok)
         objs = torch.cat(toks, dim=1).contiguous()
         drop_box_mask = True if drop_box and drop_polygons else False
         return objs.view(B * objs.shape[1], self.out_dim), B, objs.shape[1], drop_box_mask

@@ -38,18 +38,52 @@ def _launch(kind: str, flops: float, nbytes: float, fn):
 _GEMM_WS = {}
 
 
-def _ensure_gemm_workspace(device: torch.device) -> None:
-    """Register the stream-K scratch buffer with the library once per process (allocated outside any
-    CUDA-graph capture: the first GEMM of a process is never issued under capture)."""
-    if _GEMM_WS:
-        return
-    if torch.cuda.is_current_stream_capturing():
-        return
-    lib = _lib.load()
-    n = int(lib.idiff_gemm_workspace_bytes())
-    buf = torch.empty(n, dtype=torch.uint8, device=device)
-    check(lib.idiff_set_gemm_workspace(buf.data_ptr(), n), "idiff_set_gemm_workspace")
-    _GEMM_WS["buf"] = buf
+_WS_SCOPE = None  # when set (capture_workspace()), every GEMM uses this key's buffer
+
+
+def _ws_buffer(key, device: torch.device) -> torch.Tensor:
+    buf = _GEMM_WS.get(key)
+    if buf is None:
+        n = int(_lib.load().idiff_gemm_workspace_bytes())
+        buf = torch.zeros(n, dtype=torch.uint8, device=device)  # flags must start at zero
+        _GEMM_WS[key] = buf
+    return buf
+
+
+def _gemm_workspace(device: torch.device):
+    """Stream-K scratch (flags + fp32 partial tiles) for this call, passed in idiff_gemm_args.workspace:
+    one buffer per (device, stream), so GEMMs in flight on different streams never share flags.  Work
+    recorded into CUDA graphs uses one per-device buffer (`capture_workspace`): replays are ordered on
+    the replaying stream.  Never allocates during stream capture (falls back to data-parallel GEMMs)."""
+    if _WS_SCOPE is not None:
+        key = (device.index, _WS_SCOPE)
+    else:
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _GEMM_WS.get(key)
+    if buf is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None, 0
+        buf = _ws_buffer(key, device)
+    return buf.data_ptr(), buf.numel()
+
+
+class capture_workspace:
+    """Context: GEMMs issued inside (graph warm-up and capture) use the device's graph scratch buffer,
+    allocated on entry -- i.e. outside the capture."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+
+    def __enter__(self):
+        global _WS_SCOPE
+        _ws_buffer((self.device.index, "graph"), self.device)
+        self._prev, _WS_SCOPE = _WS_SCOPE, "graph"
+        return self
+
+    def __exit__(self, *exc):
+        global _WS_SCOPE
+        _WS_SCOPE = self._prev
+        return False
 
 
 def _stream() -> int:
@@ -72,7 +106,7 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
          out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          gate: float = 1.0, rowadd: Optional[torch.Tensor] = None, rows_per_batch: int = 0,
-         geglu: bool = False, silu: bool = False,
+         geglu: bool = False, silu: bool = False, gelu: bool = False,
          conv: Optional[Tuple[int, int, int, int]] = None,
          out_nchw: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epilogue(a @ w.T).  a: fp16 [M,K] (or NHWC [B,H,W,Cin] flattened with conv=(B,H,W,Cin));
@@ -80,7 +114,6 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     lib = _lib.load()
     _req(a, HALF, "a")
     _req(w, HALF, "w")
-    _ensure_gemm_workspace(a.device)
     N, K = w.shape
     if conv is not None:
         B, H, Wd, Cin = conv
@@ -96,7 +129,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         if a2.shape[1] != K:
             raise _lib.IdiffError(f"gemm: K mismatch a[{a2.shape}] w[{w.shape}]")
     n_out = N // 2 if geglu else N
-    flags = (1 if geglu else 0) | (2 if silu else 0)
+    flags = (1 if geglu else 0) | (2 if silu else 0) | (8 if gelu else 0)
     args = GemmArgs()
     if out_nchw is not None:
         _req(out_nchw, torch.float32, "out_nchw")
@@ -125,6 +158,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         args.ldr = residual.stride(0)
     args.residual = _ptr(residual)
     args.gate = float(gate)
+    args.workspace, args.workspace_bytes = _gemm_workspace(a.device)
     args.M, args.N, args.K = M, N, K
     args.lda, args.ldw = lda, w.stride(0)
     args.rows_per_batch = rows_per_batch
@@ -314,4 +348,65 @@ def silu(x: torch.Tensor) -> torch.Tensor:
     x = x.contiguous()
     out = torch.empty_like(x)
     check(lib.idiff_silu_f16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "idiff_silu_f16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# ConvNeXt mask encoder pieces (csrc/convnext.cu)
+# ------------------------------------------------------------------------------------------------
+def patchify(x: torch.Tensor, batch: int, h: int, w: int, c: int, p: int) -> torch.Tensor:
+    """NHWC fp16 [B*H*W, C] -> [B*(H/p)*(W/p), p*p*C] (operand of a kernel-p stride-p convolution)."""
+    lib = _lib.load()
+    _req(x, HALF, "x")
+    x = x.contiguous()
+    out = torch.empty((batch * (h // p) * (w // p), p * p * c), dtype=HALF, device=x.device)
+    check(lib.idiff_patchify(x.data_ptr(), out.data_ptr(), batch, h, w, c, p, _stream()), "idiff_patchify")
+    return out
+
+
+def dwconv7x7(x: torch.Tensor, w49: torch.Tensor, bias: torch.Tensor, batch: int, h: int, w: int) -> torch.Tensor:
+    """Depthwise 7x7 padding 3 on NHWC fp16 [B*H*W, C]; w49 fp32 [49, C] tap-major; bias fp32 [C]."""
+    lib = _lib.load()
+    _req(x, HALF, "x")
+    _req(w49, torch.float32, "w49")
+    _req(bias, torch.float32, "bias")
+    x = x.contiguous()
+    c = x.shape[-1]
+    out = torch.empty_like(x)
+    check(_launch("dwconv7x7", 2.0 * 49 * x.numel(), 4.0 * x.numel(), lambda: lib.idiff_dwconv7x7(
+        x.data_ptr(), w49.data_ptr(), bias.data_ptr(), out.data_ptr(), batch, h, w, c, _stream())), "idiff_dwconv7x7")
+    return out
+
+
+def segs_inconv(segs: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out_size: int):
+    """segs fp32 (B, Cin, S, S), any strides (expanded zero views included) -> (NHWC fp16
+    [B*out*out, 3] = Conv2d(Cin,3,3,1,1)(nearest-resize(segs, out)), seg_sum fp32 [B])."""
+    lib = _lib.load()
+    _req(w, torch.float32, "w")
+    _req(bias, torch.float32, "bias")
+    if not segs.is_cuda or segs.dtype != torch.float32:
+        raise _lib.IdiffError("segs must be a CUDA float32 tensor (no CPU fallback exists)")
+    B, Cin, S, S2 = segs.shape
+    if S != S2:
+        raise _lib.IdiffError("segs must be square")
+    y = torch.empty((B * out_size * out_size, 3), dtype=HALF, device=segs.device)
+    seg_sum = torch.empty((B,), dtype=torch.float32, device=segs.device)
+    strides = (C.c_long * 4)(*segs.stride())
+    check(lib.idiff_segs_inconv(segs.data_ptr(), strides, w.data_ptr(), bias.data_ptr(), y.data_ptr(),
+                                seg_sum.data_ptr(), B, Cin, S, out_size, _stream()), "idiff_segs_inconv")
+    return y, seg_sum
+
+
+def seg_tokens(feat: torch.Tensor, null_pos: torch.Tensor, pos: torch.Tensor, seg_sum: torch.Tensor, batch: int,
+               pixels: int, tokens: int) -> torch.Tensor:
+    """feat fp16 NHWC [B*P, C] -> MLP input rows fp16 [B*T, C*P/T] (token reinterpretation + null / pos)."""
+    lib = _lib.load()
+    _req(feat, HALF, "feat")
+    _req(null_pos, HALF, "null_pos")
+    _req(pos, torch.float32, "pos")
+    _req(seg_sum, torch.float32, "seg_sum")
+    c = feat.shape[-1]
+    out = torch.empty((batch * tokens, c * pixels // tokens), dtype=HALF, device=feat.device)
+    check(lib.idiff_seg_tokens(feat.data_ptr(), null_pos.data_ptr(), pos.data_ptr(), seg_sum.data_ptr(),
+                               out.data_ptr(), batch, pixels, c, tokens, _stream()), "idiff_seg_tokens")
     return out

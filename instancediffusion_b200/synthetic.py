@@ -61,9 +61,18 @@ def make_grounding_batch(batch: int, n: int, seed: int, flavor: str = "box", dev
     scribbles[:m] = lay["scribbles"][idx]
     polygons[:m] = lay["polygons"][idx]
     points[:m] = lay["points"][idx]
-    # segs: all zero (inference.py:249 discards decoded masks, so this is what the CLI feeds);
-    # a zero (1,1)-strided view keeps the (B,30,S,S) shape without 30 MiB per sample
-    segs = torch.zeros((batch, MAX_OBJS, 1, 1)).expand(batch, MAX_OBJS, seg_size, seg_size)
+    if flavor == "mask":
+        # mask conditioning (configs/test_mask.yaml): box-shaped binary masks, one (S,S) plane per slot
+        # (what decode_item.py hands to prepare_batch when the :249 mask discard is fixed)
+        seg = torch.zeros((MAX_OBJS, seg_size, seg_size))
+        for j, k in enumerate(idx):
+            x0, y0, x1, y1 = [int(round(float(v) * seg_size)) for v in lay["boxes"][k]]
+            seg[j, y0:max(y1, y0 + 1), x0:max(x1, x0 + 1)] = 1.0
+        segs = seg.unsqueeze(0).repeat(batch, 1, 1, 1)
+    else:
+        # segs: all zero (inference.py:249 discards decoded masks, so this is what the CLI feeds);
+        # a zero (1,1)-strided view keeps the (B,30,S,S) shape without 30 MiB per sample
+        segs = torch.zeros((batch, MAX_OBJS, 1, 1)).expand(batch, MAX_OBJS, seg_size, seg_size)
     rep = lambda t: t.unsqueeze(0).repeat(batch, *([1] * t.dim())).to(device)
     return {
         "boxes": rep(boxes), "masks": rep(masks), "text_masks": rep(masks), "text_embeddings": rep(text),

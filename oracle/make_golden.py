@@ -3,6 +3,7 @@ reference's own, unmodified modules (imported from $IDIFF_REF, default /root/ref
 in fp32 over the seeded cases of tests/cases.py.  Run in the authoring container:
 
     python oracle/make_golden.py [--only modules,unifusion,fourier,unet,samplers]
+    python oracle/make_golden.py --only convnext,unifusion_mask,unet_extra,samplers_extra   (round 2)
 
 The fixtures are the parity pin that travels to the GPU box (where the reference does not exist).
 """
@@ -135,12 +136,110 @@ def gen_unet_and_samplers(ref, do_unet=True, do_samplers=True):
         torch.save(out, os.path.join(GOLDEN, "samplers.pt"))
 
 
+def _set_flavor(net, flavor):
+    """configs/test_<flavor>.yaml differ only in UniFusion's test-time drop flags; the weights are the same."""
+    flags = dict(test_drop_boxes=False, test_drop_points=False, test_drop_scribbles=True, test_drop_masks=False)
+    flags.update(UNIFUSION_FLAGS[flavor])
+    for k, v in flags.items():
+        setattr(net, k, v)
+    net.test_drop_segs = flags["test_drop_masks"]
+
+
+def gen_convnext(ref):
+    from ldm.modules.diffusionmodules import convnext as cnx
+    out = {}
+    for name, spec in cases.CONVNEXT_CASES.items():
+        with ref_harness.fast_init():
+            m = getattr(cnx, spec["cls"])(*spec["args"]).eval()
+        load_synthetic(m, cases.WEIGHT_SEED, prefix=name + ".")
+        x = cases.synth_input(name, "x", spec["inputs"]["x"])
+        with torch.no_grad():
+            out[name] = m(x).float().contiguous()
+        print(f"  {name}: {tuple(out[name].shape)} absmax={out[name].abs().max():.3f}")
+    torch.save(out, os.path.join(GOLDEN, "convnext.pt"))
+
+
+def gen_unifusion_mask(ref):
+    out = {}
+    for name, spec in cases.UNIFUSION_MASK_CASES.items():
+        with ref_harness.fast_init():
+            net = ref.text_grounding_net.UniFusion(in_dim=768, out_dim=768, mid_dim=3072,
+                                                   **UNIFUSION_FLAGS[spec["flavor"]]).eval()
+        load_synthetic(net, 0, prefix="position_net.")
+        gb = synthetic.make_grounding_batch(spec["batch"], spec["n"], spec["seed"], spec["flavor"])
+        gi = ref.GroundingNetInput().prepare(gb)
+        with torch.no_grad():
+            objs, dbm = net(gi["boxes"], gi["masks"], gi["positive_embeddings"], gi["scribbles"], gi["polygons"],
+                            gi["segs"], gi["points"])
+            # intermediate: the ConvNeXt feature tokens before null substitution (debug aid for the CUDA path)
+            f = net.convnext_tiny_backbone(net.in_conv(gi["segs"]))
+        out[name] = objs.float().contiguous()
+        out[name + "/convnext_feat"] = f.float().contiguous()
+        out[name + "/drop_box_mask"] = torch.tensor(int(dbm))
+        print(f"  {name}: {tuple(objs.shape)} drop_box_mask={dbm} absmax={objs.abs().max():.3f} feat absmax={f.abs().max():.3f}")
+    torch.save(out, os.path.join(GOLDEN, "unifusion_mask.pt"))
+
+
+def gen_extra(ref, which):
+    """Round-2 fixtures: unet_extra.pt (whole-UNet eps at the bench batch and for every flavour / the
+    96x96 latent) and samplers_extra.pt (n=3 Multi-instance Sampler, the config-2 50-step latent)."""
+    t0 = time.time()
+    model = ref_harness.build_ref_unet(ref, "box", 0)
+    print(f"  reference UNet built in {time.time() - t0:.1f}s")
+    gti = model.grounding_tokenizer_input
+    diffusion = ref.LatentDiffusion(linear_start=0.00085, linear_end=0.012, timesteps=1000)
+    setter = partial(ref_harness.set_alpha_scale, ref)
+    path_u = os.path.join(GOLDEN, "unet_extra.pt")
+    path_s = os.path.join(GOLDEN, "samplers_extra.pt")
+    out_u = torch.load(path_u) if os.path.exists(path_u) else {}
+    out_s = torch.load(path_s) if os.path.exists(path_s) else {}
+    for name, spec in cases.UNET_EXTRA_CASES.items():
+        if "unet_extra" not in which and f"unet_extra:{name}" not in which:
+            continue
+        _set_flavor(model.position_net, spec["flavor"])
+        size = spec.get("size", 64)
+        inp, uc = synthetic.make_sampler_inputs(gti, spec["batch"], spec["n"], spec["seed"], spec["flavor"],
+                                                mis=False, size=size)
+        ts = torch.full((spec["batch"],), spec["t"], dtype=torch.long)
+        setter(model, 1)
+        with torch.no_grad():
+            t = time.time()
+            e = model(dict(x=inp["x"], timesteps=ts, context=inp["context"], grounding_input=inp["grounding_input"]))
+            out_u[name + "/eps_cond"] = e.float().contiguous()
+            print(f"  unet_extra {name}: eps_cond {time.time() - t:.1f}s absmax={e.abs().max():.3f}", flush=True)
+            if spec.get("uncond"):
+                e = model(dict(x=inp["x"], timesteps=ts, context=uc))
+                out_u[name + "/eps_null"] = e.float().contiguous()
+        torch.save(out_u, path_u)
+    _set_flavor(model.position_net, "box")
+    for name, sc in cases.SAMPLER_EXTRA_CASES.items():
+        if "samplers_extra" not in which and f"samplers_extra:{name}" not in which:
+            continue
+        if hasattr(model, "first_conv_state_dict"):
+            conv = torch.nn.Conv2d(4, 320, 3, padding=1)
+            conv.load_state_dict(model.first_conv_state_dict)
+            model.input_blocks[0][0] = conv
+        agen = partial(torch_oracle.alpha_schedule, alpha_type=sc["alpha_type"])
+        use_mis = sc["mis"] > 0
+        inputs, uc = synthetic.make_sampler_inputs(gti, sc["batch"], sc["n"], sc["seed"], "box", mis=use_mis)
+        if use_mis:
+            sampler = ref.PLMSSamplerInst(diffusion, model, alpha_generator_func=agen, set_alpha_scale=setter, mis=sc["mis"])
+        else:
+            sampler = ref.PLMSSampler(diffusion, model, alpha_generator_func=agen, set_alpha_scale=setter)
+        t = time.time()
+        x = sampler.sample(S=sc["S"], shape=(sc["batch"], 4, 64, 64), input=inputs, uc=uc, guidance_scale=sc["guidance"])
+        out_s[name] = x.float().contiguous()
+        print(f"  sampler {name}: {time.time() - t:.1f}s absmax={x.abs().max():.3f} finite={bool(torch.isfinite(x).all())}", flush=True)
+        torch.save(out_s, path_s)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--threads", type=int, default=os.cpu_count())
     ap.add_argument("--only", default="modules,fourier,unifusion,unet,samplers")
     args = ap.parse_args()
     only = set(args.only.split(","))
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(args.threads)
     os.makedirs(GOLDEN, exist_ok=True)
     ref = ref_harness.import_reference()
     print(f"reference at {ref.root}; torch {torch.__version__}; threads {torch.get_num_threads()}")
@@ -152,6 +251,12 @@ def main():
         print("unifusion cases"); gen_unifusion(ref)
     if "unet" in only or "samplers" in only:
         print("unet / sampler cases"); gen_unet_and_samplers(ref, "unet" in only, "samplers" in only)
+    if "convnext" in only:
+        print("convnext cases"); gen_convnext(ref)
+    if "unifusion_mask" in only:
+        print("unifusion mask cases"); gen_unifusion_mask(ref)
+    if any(o.startswith("unet_extra") or o.startswith("samplers_extra") for o in only):
+        print("round-2 unet / sampler cases"); gen_extra(ref, only)
 
 
 if __name__ == "__main__":

@@ -157,14 +157,49 @@ def fourier_embed(x, num_freqs=16, temperature=100):
     return torch.cat(out, dim=-1)
 
 
+def convnext_block(sd: SD, p: str, x):
+    """convnext.py:38-51: dwconv7x7 -> LayerNorm(C, eps 1e-6) over channels -> Linear(C,4C) -> GELU ->
+    Linear(4C,C) -> * gamma -> + input."""
+    C = x.shape[1]
+    h = F.conv2d(x, sd[p + ".dwconv.weight"], sd[p + ".dwconv.bias"], padding=3, groups=C).permute(0, 2, 3, 1)
+    h = F.layer_norm(h, (C,), sd[p + ".norm.weight"], sd[p + ".norm.bias"], 1e-6)
+    h = linear(sd, p + ".pwconv2", F.gelu(linear(sd, p + ".pwconv1", h)))
+    if p + ".gamma" in sd:
+        h = sd[p + ".gamma"] * h
+    return x + h.permute(0, 3, 1, 2)
+
+
+def _ln_channels_first(sd: SD, p: str, x, eps=1e-6):
+    """convnext.py:139-144."""
+    u = x.mean(1, keepdim=True)
+    s = (x - u).pow(2).mean(1, keepdim=True)
+    x = (x - u) / torch.sqrt(s + eps)
+    return sd[p + ".weight"][:, None, None] * x + sd[p + ".bias"][:, None, None]
+
+
+def convnext(sd: SD, p: str, x, depths=(3, 3, 9, 3)):
+    """ConvNeXt.forward_features, convnext.py:107-111 (stem :71-74, downsamplers :77-81, stages :86-92)."""
+    for i in range(4):
+        d = f"{p}.downsample_layers.{i}"
+        if i == 0:
+            x = F.conv2d(x, sd[d + ".0.weight"], sd[d + ".0.bias"], stride=4)
+            x = _ln_channels_first(sd, d + ".1", x)
+        else:
+            x = _ln_channels_first(sd, d + ".0", x)
+            x = F.conv2d(x, sd[d + ".1.weight"], sd[d + ".1.bias"], stride=2)
+        for j in range(depths[i]):
+            x = convnext_block(sd, f"{p}.stages.{i}.{j}", x)
+    return x
+
+
 def _mlp(sd: SD, p: str, x):
     """text_grounding_net.py:75-81: Linear-SiLU-Linear-SiLU-Linear."""
     return linear(sd, p + ".4", F.silu(linear(sd, p + ".2", F.silu(linear(sd, p + ".0", x)))))
 
 
 def unifusion(sd: SD, p: str, gi: Dict[str, torch.Tensor], flags: Dict[str, bool]):
-    """UniFusion.forward in eval mode, text_grounding_net.py:185-313, for all-zero `segs` (the
-    ConvNeXt branch then contributes exactly the null feature, :279-283).
+    """UniFusion.forward in eval mode, text_grounding_net.py:185-313.  All-zero `segs` contribute exactly
+    the null feature (:279-283); non-zero `segs` run the ConvNeXt mask encoder (:226-231).
     flags: test_drop_{boxes,points,scribbles,masks} of the config."""
     boxes, masks, text = gi["boxes"], gi["masks"], gi["positive_embeddings"]
     scribbles, polygons, segs, points = gi["scribbles"], gi["polygons"], gi["segs"], gi["points"]
@@ -191,9 +226,19 @@ def unifusion(sd: SD, p: str, gi: Dict[str, torch.Tensor], flags: Dict[str, bool
     e_s = sub(fourier_embed(scribbles), m_s, "null_scribble_feature")
     m_p = zeros if drop_polygons else ((polygons.sum(-1, keepdim=True) + m) > 0).float()
     e_p = sub(fourier_embed(polygons), m_p, "null_polygon_feature")
-    if not drop_segs and bool((segs.sum(dim=(1, 2, 3)) > 0).any()):
-        raise NotImplementedError("torch_oracle.unifusion: non-zero segs (ConvNeXt branch) not restated")
-    seg = sd[p + ".null_seg_feature"].view(1, 1, -1).repeat(B, 64, 1) + sd[p + ".pos_embedding"]
+    seg_null = sd[p + ".null_seg_feature"].view(1, 1, -1).repeat(B, 64, 1)
+    if p + ".in_conv.weight" in sd and not drop_segs and bool((segs.sum(dim=(1, 2, 3)) > 0).any()):
+        # :226-231: resize, 30->3 conv, ConvNeXt-tiny, NCHW (B,768,16,16) reinterpreted as (B,3072,64) -> (B,64,3072)
+        rs = F.interpolate(segs.float(), 512, mode="nearest")
+        feat = convnext(sd, p + ".convnext_tiny_backbone", F.conv2d(rs, sd[p + ".in_conv.weight"], sd[p + ".in_conv.bias"], padding=1))
+        feat = feat.reshape(B, -1, 64).permute(0, 2, 1)
+        m_seg = (rs.sum(dim=(1, 2, 3)) > 0).float().view(-1, 1, 1)           # :279
+        seg = feat * m_seg + (1 - m_seg) * seg_null + sd[p + ".pos_embedding"]  # :282-285
+    else:
+        # all-zero / dropped segs (or a state dict without the mask encoder): exactly the null feature
+        if not drop_segs and bool((segs.sum(dim=(1, 2, 3)) > 0).any()):
+            raise NotImplementedError("torch_oracle.unifusion: non-zero segs need the convnext / in_conv weights")
+        seg = seg_null + sd[p + ".pos_embedding"]
     objs = [
         _mlp(sd, p + ".linears_list.0", torch.cat([text, e_box], -1)),
         _mlp(sd, p + ".linears_list.1", torch.cat([text, e_pt], -1)),
@@ -306,8 +351,9 @@ def plms_sample(eval_fn: Callable, inputs: List[dict], uc, S: int, guidance: flo
         index = total - i - 1
         b = inp["x"].shape[0]
         x = inp["x"].clone()
-        t = torch.full((b,), int(time_range[i]), dtype=torch.long)
-        t_next = torch.full((b,), int(time_range[min(i + 1, total - 1)]), dtype=torch.long)
+        dev = inp["x"].device
+        t = torch.full((b,), int(time_range[i]), dtype=torch.long, device=dev)
+        t_next = torch.full((b,), int(time_range[min(i + 1, total - 1)]), dtype=torch.long, device=dev)
         at, ap = a[index], a_prev[index]
 
         def x_prev_of(e):

@@ -63,6 +63,17 @@ UNIFUSION_CASES = {
     "unifusion_point": dict(flavor="point", batch=2, n=3, seed=6),
     "unifusion_scribble": dict(flavor="scribble", batch=2, n=3, seed=7),
 }
+# mask flavour: 256-point polygons + box-shaped binary `segs` through the ConvNeXt mask encoder
+# (text_grounding_net.py:226-231, 277-287); fixture unifusion_mask.pt
+UNIFUSION_MASK_CASES = {
+    "unifusion_mask": dict(flavor="mask", batch=2, n=3, seed=8),
+}
+# ConvNeXt pieces (convnext.py:15-123); fixture convnext.pt.  `fn` names a module-level callable.
+CONVNEXT_CASES = {
+    "convnext_block96": dict(cls="Block", args=(96,), inputs=dict(x=(2, 96, 16, 16))),
+    "convnext_block768": dict(cls="Block", args=(768,), inputs=dict(x=(1, 768, 8, 8))),
+    "convnext_tiny": dict(cls="ConvNeXt", args=(), inputs=dict(x=(1, 3, 64, 64))),
+}
 
 # whole-UNet cases (B=1, 64x64 latent, box flavour, 2 instances)
 UNET_CASE = dict(flavor="box", batch=1, n=2, seed=11, t=601, weight_seed=0)
@@ -71,6 +82,22 @@ UNET_CASE = dict(flavor="box", batch=1, n=2, seed=11, t=601, weight_seed=0)
 SAMPLER_CASES = {
     "plms_S4": dict(S=4, n=1, mis=0.0, batch=1, seed=21, guidance=7.5, alpha_type=[0.8, 0.0, 0.2]),
     "mis_S10": dict(S=10, n=1, mis=0.36, batch=1, seed=22, guidance=7.5, alpha_type=[0.8, 0.0, 0.2]),
+}
+
+# round-2 additions (fixtures unet_extra.pt / samplers_extra.pt): the configuration bench.py runs
+# (config 2: forward batch 4+4, 8 instances, 50 steps), a Multi-instance Sampler run that merges
+# more than two latents, the point / scribble / mask flavours through the whole UNet, a 96x96 latent
+# (768^2 images, config 4: non-power-of-two maps take the reference's fp32 FFT branch).
+UNET_EXTRA_CASES = {
+    "b4n8": dict(flavor="box", batch=4, n=8, seed=31, t=601, uncond=True),
+    "point": dict(flavor="point", batch=1, n=2, seed=12, t=401),
+    "scribble": dict(flavor="scribble", batch=1, n=2, seed=13, t=801),
+    "mask": dict(flavor="mask", batch=1, n=2, seed=14, t=601),
+    "lat96": dict(flavor="box", batch=1, n=2, seed=15, t=601, size=96),
+}
+SAMPLER_EXTRA_CASES = {
+    "mis_S10_n3": dict(S=10, n=3, mis=0.36, batch=1, seed=23, guidance=7.5, alpha_type=[0.8, 0.0, 0.2]),
+    "plms_S50_b4": dict(S=50, n=8, mis=0.0, batch=4, seed=24, guidance=7.5, alpha_type=[0.8, 0.0, 0.2]),
 }
 
 

@@ -40,7 +40,7 @@ def test_struct_layout_matches_header():
         decl = decl.strip()
         if not decl:
             continue
-        decl = re.sub(r"^(const\s+)?(void|float|int)\s*\*?", "", decl)
+        decl = re.sub(r"^(const\s+)?(void|float|int|long)\s*\*?", "", decl)
         names += [n.strip().lstrip("*") for n in decl.split(",") if n.strip()]
     assert names == [f[0] for f in _lib.GemmArgs._fields_], names
 
@@ -187,6 +187,65 @@ def test_dropin_install_resolves_reference_paths():
         "print('ok')\n" % ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_dropin_keeps_reference_packages_as_parents():
+    """With the reference checkout on sys.path, install() must shadow only the hot-path leaf modules:
+    the reference's inference.py import block (:14-22) and every `target:` of configs/test_box.yaml
+    (:2,9,27,43,64,76) keep resolving -- non-mirrored modules from the reference's own files.  A module
+    may fail only on its *own* third-party dependency missing in this container (clip, kornia,
+    omegaconf, pycocotools, skimage)."""
+    import subprocess
+    ref = os.environ.get("IDIFF_REF", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "ldm")):
+        pytest.skip("reference checkout not present")
+    code = r"""
+import sys, importlib
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from instancediffusion_b200 import dropin
+root = dropin.install()
+assert root is not None
+THIRD = ("clip", "kornia", "omegaconf", "pycocotools", "skimage", "tkinter", "diffusers", "torchvision", "tensorboard")
+def imp(name):
+    try:
+        return importlib.import_module(name)
+    except ImportError as e:
+        assert (e.name or "").split(".")[0] in THIRD, (name, e)
+        print("own-dependency", name, e.name)
+        return None
+import ldm.modules.attention as A, instancediffusion_b200.ldm.modules.attention as B
+assert A is B
+ae = imp("ldm.models.autoencoder"); assert ae is not None and ae.__file__.startswith(root)
+dm = imp("ldm.modules.diffusionmodules.model"); assert dm is not None and dm.__file__.startswith(root)
+assert dm.LinearAttention.__module__.endswith("ldm.modules.attention")   # served by the reference's own file
+imp("ldm.modules.encoders.modules")
+imp("utils.input"); imp("utils.checkpoint"); imp("dataset.decode_item")
+from ldm.util import instantiate_from_config, get_obj_from_str
+ours = {"ldm.models.diffusion.ldm.LatentDiffusion", "ldm.modules.diffusionmodules.openaimodel.UNetModel",
+        "ldm.modules.diffusionmodules.text_grounding_net.UniFusion",
+        "grounding_input.text_grounding_tokinzer_input.GroundingNetInput"}
+for t in ours:
+    assert get_obj_from_str(t).__module__.startswith("instancediffusion_b200."), t
+assert get_obj_from_str("ldm.models.autoencoder.AutoencoderKL").__module__ == "ldm.models.autoencoder"
+try:
+    get_obj_from_str("ldm.modules.encoders.modules.FrozenCLIPEmbedder")
+except ImportError as e:
+    assert (e.name or "").split(".")[0] in THIRD, e
+from ldm.models.diffusion.plms import PLMSSampler
+from ldm.models.diffusion.plms_instance import PLMSSamplerInst
+assert PLMSSamplerInst.__module__.startswith("instancediffusion_b200.")
+from utils.model import set_alpha_scale, alpha_generator
+assert set_alpha_scale.__module__.startswith("instancediffusion_b200.")
+try:
+    from utils.model import create_clip_pretrain_model   # inference.py:22
+except ImportError as e:
+    assert any(t in str(e) for t in THIRD), e
+dropin.uninstall()
+assert "ldm.modules.attention" not in sys.modules
+print("ok")
+""" % (ref, ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd="/tmp")
+    assert r.returncode == 0 and "ok" in r.stdout, (r.stdout[-1500:], r.stderr[-2500:])
 
 
 # ------------------------------------------------------------------------------------------------

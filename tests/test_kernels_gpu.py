@@ -412,3 +412,70 @@ def test_plms_update_and_mean(cuda_device):
     m = torch.empty_like(x)
     ops.latent_mean([x, ec, eu], m)
     _check(m, (x + ec + eu) / 3, 1e-6, 1e-6, "latent mean")
+
+
+# --------------------------------------------------------------------------------------------
+# ConvNeXt mask-encoder pieces (csrc/convnext.cu) and the GELU epilogue
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(16384, 96, 48), (1024, 384, 96), (256, 768, 3072), (300, 192, 384)])
+def test_gemm_gelu_epilogue_small_k_n(cuda_device, M, N, K):
+    """pwconv1 (GELU fused) and the patchify GEMMs: N < one tile, K = 48 < one 64-wide k-block."""
+    ops = _ops()
+    a = _randn((M, K), cuda_device, 1.0, 1).half()
+    w = _randn((N, K), cuda_device, 1.0 / math.sqrt(K), 2).half()
+    bias = _randn((N,), cuda_device, 0.5, 3)
+    ref = F.gelu(a.float() @ w.float().t() + bias)
+    _check(ops.gemm(a, w, bias, gelu=True), ref, 2e-3, 2e-3, f"gemm+gelu {M}x{N}x{K}")
+    _check(ops.gemm(a, w, bias), a.float() @ w.float().t() + bias, 2e-3, 2e-3, f"gemm {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 96), (1, 128, 128, 96), (2, 8, 8, 768), (1, 5, 7, 192)])
+def test_dwconv7x7(cuda_device, B, H, W, C):
+    ops = _ops()
+    x = _randn((B, C, H, W), cuda_device, 1.0, 4).half()
+    w = _randn((C, 1, 7, 7), cuda_device, 1.0 / 7, 5)
+    b = _randn((C,), cuda_device, 0.1, 6)
+    ref = F.conv2d(x.float(), w, b, padding=3, groups=C).permute(0, 2, 3, 1).reshape(B * H * W, C)
+    x16 = x.permute(0, 2, 3, 1).reshape(B * H * W, C).contiguous()
+    out = ops.dwconv7x7(x16, w.reshape(C, 49).t().contiguous(), b, B, H, W)
+    _check(out, ref, 2e-3, 2e-3, f"dwconv7x7 {B}x{H}x{W}x{C}")
+
+
+@pytest.mark.parametrize("B,H,W,C,p", [(2, 16, 16, 3, 4), (1, 8, 8, 96, 2), (2, 4, 12, 384, 2)])
+def test_patchify(cuda_device, B, H, W, C, p):
+    ops = _ops()
+    x = _randn((B, H, W, C), cuda_device, 1.0, 7).half()
+    out = ops.patchify(x.reshape(B * H * W, C), B, H, W, C, p)
+    ref = x.view(B, H // p, p, W // p, p, C).permute(0, 1, 3, 2, 4, 5).reshape(B * (H // p) * (W // p), p * p * C)
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("S", [512, 256, 100])
+def test_segs_inconv_and_seg_tokens(cuda_device, S):
+    ops = _ops()
+    B, CI, R = 2, 30, 512
+    segs = torch.zeros((B, CI, S, S), device=cuda_device)
+    segs[0, 0, S // 8: S // 2, S // 4: S // 2] = 1.0
+    segs[0, 3, : S // 3, : S // 5] = 1.0          # sample 1 stays all zero
+    w = _randn((3, CI, 3, 3), cuda_device, 0.2, 8)
+    b = _randn((3,), cuda_device, 0.1, 9)
+    y, seg_sum = ops.segs_inconv(segs, w, b, R)
+    rs = F.interpolate(segs, R, mode="nearest")
+    ref = F.conv2d(rs, w, b, padding=1).permute(0, 2, 3, 1).reshape(B * R * R, 3)
+    _check(y, ref, 1e-3, 1e-3, f"segs_inconv S={S}")
+    assert torch.allclose(seg_sum, rs.sum(dim=(1, 2, 3)), rtol=1e-5), (seg_sum, rs.sum(dim=(1, 2, 3)))
+    # expanded zero view (what the null / box-only inputs carry): strides are honoured
+    zv = torch.zeros((B, CI, 1, 1), device=cuda_device).expand(B, CI, S, S)
+    y0, s0 = ops.segs_inconv(zv, w, b, R)
+    assert float(s0.abs().max()) == 0.0
+    _check(y0, b.view(1, 3).expand(B * R * R, 3), 1e-3, 1e-3, "segs_inconv zero view")
+    # token reinterpretation: reshape(B, -1, T).permute(0, 2, 1) of the NCHW feature map
+    P, C, T = 256, 768, 64
+    feat = _randn((B, C, 16, 16), cuda_device, 1.0, 10).half()
+    pos = _randn((T, C * P // T), cuda_device, 0.5, 11)
+    null_pos = _randn((T, C * P // T), cuda_device, 1.0, 12).half()
+    nhwc = feat.permute(0, 2, 3, 1).reshape(B * P, C).contiguous()
+    out = ops.seg_tokens(nhwc, null_pos, pos, seg_sum, B, P, T).view(B, T, -1)
+    ref0 = feat.float().reshape(B, -1, T).permute(0, 2, 1)[0] + pos
+    _check(out[0], ref0, 1e-3, 1e-3, "seg_tokens has-seg sample")
+    assert torch.equal(out[1], null_pos)

@@ -83,6 +83,51 @@ def test_unifusion_matches_reference_golden(cuda_device, name):
     assert int(dbm) == int(gold[name + "/drop_box_mask"])
 
 
+@pytest.mark.parametrize("name", list(cases.CONVNEXT_CASES))
+def test_convnext_matches_reference_golden(cuda_device, name):
+    """ConvNeXt Block / the whole ConvNeXt-tiny trunk vs the reference's convnext.py (CPU fp32)."""
+    from instancediffusion_b200.ldm.modules.diffusionmodules import convnext as cnx
+    from instancediffusion_b200.weights import load_synthetic
+    gold = _load("convnext.pt")
+    spec = cases.CONVNEXT_CASES[name]
+    m = getattr(cnx, spec["cls"])(*spec["args"])
+    load_synthetic(m, cases.WEIGHT_SEED, prefix=name + ".")
+    m = m.to(cuda_device).eval()
+    x = cases.synth_input(name, "x", spec["inputs"]["x"]).to(cuda_device)
+    with torch.no_grad():
+        out = m(x)
+    # a Block is 2 GEMMs deep (3e-3 like the other modules); the trunk chains 18 blocks + 4 strided convs
+    _report(out, gold[name], name, 3e-3 if "block" in name else 6e-3, 2e-2)
+
+
+@pytest.mark.parametrize("name", list(cases.UNIFUSION_MASK_CASES))
+def test_unifusion_mask_matches_reference_golden(cuda_device, name):
+    """Mask conditioning: non-zero `segs` through in_conv + ConvNeXt + the 64 mask tokens
+    (text_grounding_net.py:226-231, 277-287), polygons live."""
+    from instancediffusion_b200 import synthetic
+    from instancediffusion_b200.grounding_input.text_grounding_tokinzer_input import GroundingNetInput
+    from instancediffusion_b200.ldm.modules.diffusionmodules.text_grounding_net import UniFusion
+    from instancediffusion_b200.weights import UNIFUSION_FLAGS, load_synthetic
+    gold = _load("unifusion_mask.pt")
+    spec = cases.UNIFUSION_MASK_CASES[name]
+    with torch.device("meta"):
+        net = UniFusion(in_dim=768, out_dim=768, mid_dim=3072, **UNIFUSION_FLAGS[spec["flavor"]])
+    net = net.to_empty(device=cuda_device).eval()
+    load_synthetic(net, 0, prefix="position_net.")
+    gb = synthetic.make_grounding_batch(spec["batch"], spec["n"], spec["seed"], spec["flavor"], device=cuda_device)
+    gi = GroundingNetInput().prepare(gb)
+    # the ConvNeXt feature map on its own first (localises a failure)
+    y, seg_sum = __import__("instancediffusion_b200.ops", fromlist=["x"]).segs_inconv(
+        gi["segs"].float(), net.pk()["w_inconv"], net.pk()["b_inconv"], 512)
+    feat, fh, fw = net.convnext_tiny_backbone._features(y, spec["batch"], 512, 512)
+    ref_feat = gold[name + "/convnext_feat"]
+    _report(feat.view(spec["batch"], fh, fw, -1).permute(0, 3, 1, 2), ref_feat, name + "/convnext_feat", 6e-3, 3e-2)
+    objs, dbm = net(gi["boxes"], gi["masks"], gi["positive_embeddings"], gi["scribbles"], gi["polygons"],
+                    gi["segs"], gi["points"])
+    _report(objs, gold[name], name, 4e-3, 2e-2)
+    assert int(dbm) == int(gold[name + "/drop_box_mask"])
+
+
 # --------------------------------------------------------------------------------------------
 # whole UNet + samplers (synthetic weights regenerated bit-identically from the seed)
 # --------------------------------------------------------------------------------------------
@@ -114,24 +159,29 @@ def test_unet_eps_matches_reference_golden(cuda_device, unet):
     objs, _ = unet.position_net(gi["boxes"], gi["masks"], gi["positive_embeddings"], gi["scribbles"], gi["polygons"],
                                 gi["segs"], gi["points"])
     _report(objs, gold["objs"], "unet/objs", 3e-3, 1e-2)
-    # one full denoise forward: ~200 fp16 layers deep.  2e-2 relative L2 is the fp16 envelope we hold
-    # ourselves to; the measured value is printed (and recorded in DESIGN.md).
+    # one full denoise forward: ~200 fp16 layers deep.  Measured 2.0e-3 relative L2;
+    # the bound is 2x that.  (The reference itself under autocast(fp16) deviates as much:
+    # tests/test_parity_r2_gpu.py::test_fp16_envelope_eps_and_latents.)
     for graph in (False, True):
         unet.use_cuda_graph = graph
         eps_c = unet(dict(x=inp["x"], timesteps=ts, context=inp["context"], grounding_input=gi))
-        _report(eps_c, gold["eps_cond"], f"unet/eps_cond graph={graph}", 2e-2, 5e-2)
+        _report(eps_c, gold["eps_cond"], f"unet/eps_cond graph={graph}", 4e-3, 2e-2)
         eps_u = unet(dict(x=inp["x"], timesteps=ts, context=uc))
-        _report(eps_u, gold["eps_null"], f"unet/eps_null graph={graph}", 2e-2, 5e-2)
-    # batched cond+uncond == separate forwards (per-sample independence of every op)
+        _report(eps_u, gold["eps_null"], f"unet/eps_null graph={graph}", 4e-3, 2e-2)
+    # batched cond+uncond: every row against the *reference golden* (not against our own single path), same
+    # bound.  Tile widths / stream-K splits depend on M, so batched and single runs round differently at the
+    # fp16 level and are not bit-equal; both must sit inside the same distance of the fp32 reference.
     both = unet.forward_batched([dict(x=inp["x"], timesteps=ts, context=inp["context"], grounding_input=gi),
                                  dict(x=inp["x"], timesteps=ts, context=uc)])
-    _report(both[0], eps_c.cpu(), "batched cond == single", 1e-2, 2e-2)
-    _report(both[1], eps_u.cpu(), "batched uncond == single", 1e-2, 2e-2)
+    _report(both[0], gold["eps_cond"], "batched cond vs golden", 4e-3, 2e-2)
+    _report(both[1], gold["eps_null"], "batched uncond vs golden", 4e-3, 2e-2)
+    _report(both[0], eps_c.cpu(), "batched cond vs single", 4e-3, 2e-2)
+    _report(both[1], eps_u.cpu(), "batched uncond vs single", 4e-3, 2e-2)
     # alpha = 0: fusers off + SD1.5 first conv (openaimodel.py:469-480)
     set_alpha_scale(unet, 0)
     unet.set_sd_first_conv(unet._sd_conv)
     eps_0 = unet(dict(x=inp["x"], timesteps=ts, context=inp["context"], grounding_input=gi))
-    _report(eps_0, gold["eps_alpha0"], "unet/eps_alpha0", 2e-2, 5e-2)
+    _report(eps_0, gold["eps_alpha0"], "unet/eps_alpha0", 4e-3, 2e-2)
     unet.undo_first_conv_restore()
     set_alpha_scale(unet, 1)
 
@@ -140,8 +190,9 @@ def test_unet_eps_matches_reference_golden(cuda_device, unet):
 def test_sampler_latent_vs_reference_golden(cuda_device, unet, name):
     """End-to-end latent after the full PLMS / Multi-instance loop (config 1 of BASELINE.json for
     mis_S10).  north_star's rtol=1e-3/atol=1e-4 on the latent is tighter than fp16 re-association
-    noise compounded over 10-30 CFG-7.5 forwards (SURVEY.md section 7 'hard parts'); the bound held
-    here is 5e-2 relative L2 vs the fp32 reference, the measured value is printed."""
+    noise compounded over 10-30 CFG-7.5 forwards (measured for the reference's own arithmetic under
+    autocast(fp16) in tests/test_parity_r2_gpu.py); the bound held here is 8e-3 relative L2 vs the fp32
+    reference = 2x the measured value, which is printed."""
     from functools import partial
     from instancediffusion_b200 import synthetic
     from instancediffusion_b200.ldm.models.diffusion.ldm import LatentDiffusion
@@ -173,4 +224,4 @@ def test_sampler_latent_vs_reference_golden(cuda_device, unet, name):
         unet.restore_first_conv_from_SD = orig
         unet.undo_first_conv_restore()
         set_alpha_scale(unet, 1)
-    _report(x, gold[name], f"sampler/{name}", 5e-2, 1.5e-1)
+    _report(x, gold[name], f"sampler/{name}", 8e-3, 5e-2)  # measured 2.8-3.7e-3

@@ -111,6 +111,38 @@ def test_unifusion_restatement_matches_reference(name):
     assert int(dbm) == int(gold[name + "/drop_box_mask"])
 
 
+@pytest.mark.parametrize("name", list(cases.CONVNEXT_CASES))
+def test_convnext_restatement_matches_reference(name):
+    gold = _load("convnext.pt")
+    spec = cases.CONVNEXT_CASES[name]
+    from instancediffusion_b200.ldm.modules.diffusionmodules import convnext as cnx
+    with torch.device("meta"):
+        m = getattr(cnx, spec["cls"])(*spec["args"])
+    sd = {"m." + k: synth_tensor(f"{name}.{k}", tuple(v.shape), cases.WEIGHT_SEED) for k, v in m.state_dict().items()}
+    x = cases.synth_input(name, "x", spec["inputs"]["x"])
+    with torch.no_grad():
+        out = TO.convnext_block(sd, "m", x) if spec["cls"] == "Block" else TO.convnext(sd, "m", x)
+    _close(out, gold[name], 1e-4, 2e-5, name)
+
+
+@pytest.mark.parametrize("name", list(cases.UNIFUSION_MASK_CASES))
+def test_unifusion_mask_restatement_matches_reference(name):
+    """Non-zero `segs`: in_conv + ConvNeXt + token reinterpretation of the oracle port vs the reference."""
+    gold = _load("unifusion_mask.pt")
+    spec = cases.UNIFUSION_MASK_CASES[name]
+    from instancediffusion_b200.ldm.modules.diffusionmodules.text_grounding_net import UniFusion
+    with torch.device("meta"):
+        net = UniFusion(in_dim=768, out_dim=768, mid_dim=3072)
+    sd = {"position_net." + k: synth_tensor("position_net." + k, tuple(v.shape), 0) for k, v in net.state_dict().items()}
+    gb = synthetic.make_grounding_batch(spec["batch"], spec["n"], spec["seed"], spec["flavor"])
+    gi = dict(boxes=gb["boxes"], masks=gb["masks"], positive_embeddings=gb["text_embeddings"],
+              scribbles=gb["scribbles"], polygons=gb["polygons"], segs=gb["segs"], points=gb["points"])
+    with torch.no_grad():
+        objs, dbm = TO.unifusion(sd, "position_net", gi, UNIFUSION_FLAGS[spec["flavor"]])
+    _close(objs, gold[name], 1e-4, 2e-5, name)
+    assert int(dbm) == int(gold[name + "/drop_box_mask"])
+
+
 def test_schema_matches_reference():
     """The mirror UNetModel exposes exactly the reference's 1199 state_dict keys and shapes
     (utils/checkpoint.py:241-244 loads strict)."""
@@ -129,3 +161,71 @@ def test_schema_matches_reference():
     bad = [k for k in ours if ours[k] != ref_schema[k]]
     assert not bad, bad[:10]
     assert list(ours) == list(ref_schema), "key order differs"
+
+
+# ------------------------------------------------------------------------------------------------
+# whole-UNet and sampler restatements (what bench.py's CPU arm and smoke() execute) pinned to the
+# reference's own outputs
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def unet_sd():
+    import json
+    path = os.path.join(GOLDEN, "unet_schema.json")
+    if not os.path.exists(path):
+        pytest.skip("unet_schema.json not generated")
+    schema = json.load(open(path))
+    return {k: synth_tensor(k, tuple(s), cases.UNET_CASE["weight_seed"]) for k, s in schema.items()}
+
+
+def _rel_l2(got, ref):
+    return ((got - ref).norm() / ref.norm()).item()
+
+
+def _gti():
+    from instancediffusion_b200.grounding_input.text_grounding_tokinzer_input import GroundingNetInput
+    return GroundingNetInput()
+
+
+def test_unet_forward_restatement_matches_reference(unet_sd):
+    """oracle/torch_oracle.py:unet_forward vs the reference's UNetModel.forward (tests/golden/unet.pt):
+    fp32 vs fp32, only the summation order of a few fused expressions differs."""
+    gold = _load("unet.pt")
+    spec = cases.UNET_CASE
+    inp, uc = synthetic.make_sampler_inputs(_gti(), spec["batch"], spec["n"], spec["seed"], spec["flavor"], mis=False)
+    ts = torch.full((spec["batch"],), spec["t"], dtype=torch.long)
+    gi = inp["grounding_input"]
+    flags = UNIFUSION_FLAGS[spec["flavor"]]
+    sd15 = _load("sd15_first_conv.pt")
+    with torch.no_grad():
+        e_c = TO.unet_forward(unet_sd, inp["x"], ts, inp["context"], gi, flags)
+        e_u = TO.unet_forward(unet_sd, inp["x"], ts, uc, TO.null_grounding_input(gi), flags)
+        e_0 = TO.unet_forward(unet_sd, inp["x"], ts, inp["context"], gi, flags, scale=0.0, first_conv=sd15)
+    for got, key in ((e_c, "eps_cond"), (e_u, "eps_null"), (e_0, "eps_alpha0")):
+        rel = _rel_l2(got, gold[key])
+        print(f"[oracle unet_forward] {key}: rel_l2 {rel:.2e}")
+        assert rel < 1e-4, (key, rel)
+        _close(got, gold[key], 1e-3, 1e-4, key)  # north_star's latent tolerance, met fp32-vs-fp32
+
+
+@pytest.mark.parametrize("name", list(cases.SAMPLER_CASES))
+def test_plms_sample_restatement_matches_reference(unet_sd, name):
+    """oracle/torch_oracle.py:plms_sample (PLMS and the Multi-instance Sampler) vs the latents the
+    reference's PLMSSampler / PLMSSamplerInst produced (tests/golden/samplers.pt)."""
+    gold = _load("samplers.pt")
+    sc = cases.SAMPLER_CASES[name]
+    sd15 = _load("sd15_first_conv.pt")
+    flags = UNIFUSION_FLAGS["box"]
+    inputs, uc = synthetic.make_sampler_inputs(_gti(), sc["batch"], sc["n"], sc["seed"], "box", mis=sc["mis"] > 0)
+    inputs = inputs if isinstance(inputs, list) else [inputs]
+    null_gi = TO.null_grounding_input(inputs[0]["grounding_input"])
+
+    def eval_fn(inp, alpha):
+        gi = inp.get("grounding_input")
+        return TO.unet_forward(unet_sd, inp["x"], inp["timesteps"], inp["context"], gi if gi is not None else null_gi,
+                               flags, scale=float(alpha), first_conv=sd15 if alpha == 0 else None)
+
+    with torch.no_grad():
+        x = TO.plms_sample(eval_fn, inputs, uc, sc["S"], sc["guidance"], sc["mis"], alpha_type=sc["alpha_type"])
+    rel = _rel_l2(x, gold[name])
+    print(f"[oracle plms_sample] {name}: rel_l2 {rel:.2e}")
+    assert rel < 2e-4, rel
