@@ -30,6 +30,23 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = "config2: batch=4 512x512, 8 box instances, 50-step PLMS, CFG 7.5, fp16, 1 GPU"
 BATCH, N_INST, S_STEPS, GUIDANCE, ALPHA_TYPE = 4, 8, 50, 7.5, [0.8, 0.0, 0.2]
+FLAVOR, LATENT = "box", 64
+MIS_DEFAULT = 0.36  # inference.py:176
+
+# BASELINE.json configs (per GPU; every config shards whole images over ranks, no per-step collective).
+# Config 2 is the headline the metric is quoted on; the others are selectable parity / stress workloads.
+CONFIGS = {
+    2: dict(workload=WORKLOAD, batch=4, n=8, flavor="box", latent=64, mis=0.0),
+    3: dict(workload="config3: batch=4 per GPU (32 over 8 GPUs) 512x512, box+point+scribble (test_scribble flags), "
+                     "8 instances, 50-step PLMS, Multi-instance Sampler 0.36, alpha 0.8, fp16",
+            batch=4, n=8, flavor="scribble", latent=64, mis=0.36),
+    4: dict(workload="config4: batch=8 768x768 (latent 96x96), mask conditioning (test_mask flags), 16 instances, "
+                     "50-step PLMS, fp16 arithmetic (BASELINE names bf16; this library computes in fp16)",
+            batch=8, n=16, flavor="mask", latent=96, mis=0.0),
+    5: dict(workload="config5: batch=8 per GPU (64 over 8 GPUs) 512x512, 30 box instances, 50-step PLMS, "
+                     "Multi-instance Sampler 0.36 (31 trajectories), fp16",
+            batch=8, n=30, flavor="box", latent=64, mis=0.36),
+}
 
 
 def forwards_per_sample_call(S, n, mis):
@@ -193,8 +210,14 @@ def build_pipeline(device, rank, world):
     from instancediffusion_b200.ldm.models.diffusion.ldm import LatentDiffusion
     from instancediffusion_b200.weights import build_unet
     # rank 0 materialises the synthetic weights; the other ranks receive them over NCCL
-    model = build_unet("box", device, seed=0 if rank == 0 else None)
-    sent = parallel.broadcast_module_(model, src=0)
+    model = build_unet(FLAVOR, device, seed=0 if rank == 0 else None)
+    torch.cuda.synchronize()
+    parallel.barrier()
+    t0 = time.perf_counter()
+    sent = parallel.broadcast_module_(model, src=0)  # matrices as fp16 (2.46 GB), vectors fp32
+    torch.cuda.synchronize()
+    parallel.barrier()
+    bcast_ms = (time.perf_counter() - t0) * 1e3 if world > 1 else 0.0
     diffusion = LatentDiffusion(linear_start=0.00085, linear_end=0.012, timesteps=1000).to(device)
     # SD1.5 first conv swapped in at alpha == 0 (openaimodel.py:469-480).  The shipped 48 KB file is
     # a fixture under tests/golden/; a synthetic stand-in of the same shape is used if it is absent.
@@ -206,7 +229,7 @@ def build_pipeline(device, rank, world):
         sd_conv = {"weight": torch.randn((320, 4, 3, 3), generator=g) * 0.1, "bias": torch.zeros(320)}
     model.restore_first_conv_from_SD = lambda: (None if getattr(model, "_first_conv_restored", False)
                                                 else model.set_sd_first_conv(sd_conv))
-    return model, diffusion, sent
+    return model, diffusion, sent, bcast_ms
 
 
 def make_sampler(model, diffusion, mis):
@@ -224,7 +247,7 @@ def host_inputs(model, seed, mis):
     to the device inside the timed region)."""
     from instancediffusion_b200 import synthetic
     gti = model.grounding_tokenizer_input
-    inputs, uc = synthetic.make_sampler_inputs(gti, BATCH, N_INST, seed, "box", mis=mis > 0, device="cpu")
+    inputs, uc = synthetic.make_sampler_inputs(gti, BATCH, N_INST, seed, FLAVOR, mis=mis > 0, device="cpu", size=LATENT)
     lst = inputs if isinstance(inputs, list) else [inputs]
 
     def pin(t):
@@ -267,7 +290,7 @@ def roofline_pass(model, device, peaks):
     from instancediffusion_b200 import ops, synthetic
     from instancediffusion_b200.utils.model import set_alpha_scale
     gti = model.grounding_tokenizer_input
-    inp, uc = synthetic.make_sampler_inputs(gti, BATCH, N_INST, 77, "box", mis=False, device=device)
+    inp, uc = synthetic.make_sampler_inputs(gti, BATCH, N_INST, 77, FLAVOR, mis=False, device=device, size=LATENT)
     inp["timesteps"] = torch.full((BATCH,), 601, dtype=torch.long, device=device)
     un = dict(x=inp["x"], timesteps=inp["timesteps"], context=uc)
     set_alpha_scale(model, 1)
@@ -335,14 +358,23 @@ def roofline_pass(model, device, peaks):
 
 
 def main():
+    global WORKLOAD, BATCH, N_INST, FLAVOR, LATENT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--mis", type=float, default=0.0, help="Multi-instance Sampler fraction (inference.py default 0.36)")
+    ap.add_argument("--mis", type=float, default=None,
+                    help="Multi-instance Sampler fraction of the headline leg (inference.py default 0.36); default: the "
+                         "config's own (0 for config 2, whose plain-PLMS number is BASELINE's metric)")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[N-1]")
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mis-leg", action="store_true", help="skip the extra mis=0.36 leg of config 2")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    WORKLOAD, BATCH, N_INST, FLAVOR, LATENT = cfg["workload"], cfg["batch"], cfg["n"], cfg["flavor"], cfg["latent"]
+    if args.mis is None:
+        args.mis = cfg["mis"]
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -360,12 +392,9 @@ def main():
     except Exception:
         pass
 
-    model, diffusion, sent = build_pipeline(device, rank, world)
-    sampler = make_sampler(model, diffusion, args.mis)
+    model, diffusion, sent, bcast_ms = build_pipeline(device, rank, world)
     gti = model.grounding_tokenizer_input
-    host, uc_host, is_list = host_inputs(model, 1000 + rank, args.mis)
-    shape = (BATCH, 4, 64, 64)
-    fpc = forwards_per_sample_call(S_STEPS, N_INST, args.mis)
+    shape = (BATCH, 4, LATENT, LATENT)
 
     def reset():
         # every sample() call starts from a fresh model state and recomputes the per-sample hoisted
@@ -375,83 +404,104 @@ def main():
         model._ctx_cache.clear()
         model._obj_cache.clear()
 
-    def run_resident(inputs, uc):
-        # fresh trajectory state; the latent x is cloned so every step starts from the same noise
-        if isinstance(inputs, list):
-            ins = [dict(i, x=i["x"].clone()) for i in inputs]
-        else:
-            ins = dict(inputs, x=inputs["x"].clone())
-        return sampler.sample(S=S_STEPS, shape=shape, input=ins, uc=uc, guidance_scale=GUIDANCE)
+    def measure(mis, steps, warmup):
+        """One leg: `warmup` untimed + `steps` timed sample() calls with inputs resident in HBM, then `steps`
+        timed calls end to end (pinned host buffers in, latent back to the host inside the timed region).
+        Device-timed with CUDA events, barrier + synchronize on both sides, max over ranks."""
+        sampler = make_sampler(model, diffusion, mis)
+        host, uc_host, is_list = host_inputs(model, 1000 + rank, mis)
 
-    # ---- device-resident leg -------------------------------------------------------------------
-    dev_inputs, uc_dev, h2d_bytes = to_device(host, uc_host, is_list, device, gti)
-    torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        reset()
-        run_resident(dev_inputs, uc_dev)
-    torch.cuda.synchronize()
-    parallel.barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    with ClockSampler(local_rank) as clk:
+        def run_resident(inputs, uc):
+            # fresh trajectory state; the latent x is cloned so every step starts from the same noise
+            if isinstance(inputs, list):
+                ins = [dict(i, x=i["x"].clone()) for i in inputs]
+            else:
+                ins = dict(inputs, x=inputs["x"].clone())
+            return sampler.sample(S=S_STEPS, shape=shape, input=ins, uc=uc, guidance_scale=GUIDANCE)
+
+        dev_inputs, uc_dev, h2d_bytes = to_device(host, uc_host, is_list, device, gti)
         torch.cuda.synchronize()
-        ev[0].record()
-        for _ in range(args.steps):
+        for _ in range(warmup):
             reset()
-            out = run_resident(dev_inputs, uc_dev)
-        ev[1].record()
+            run_resident(dev_inputs, uc_dev)
         torch.cuda.synchronize()
-    parallel.barrier()
-    t_dev = parallel.max_over_ranks(ev[0].elapsed_time(ev[1]) * 1e-3, device)
-    assert torch.isfinite(out).all()
+        parallel.barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        with ClockSampler(local_rank) as clk:
+            torch.cuda.synchronize()
+            ev[0].record()
+            for _ in range(steps):
+                reset()
+                out = run_resident(dev_inputs, uc_dev)
+            ev[1].record()
+            torch.cuda.synchronize()
+        parallel.barrier()
+        t_dev = parallel.max_over_ranks(ev[0].elapsed_time(ev[1]) * 1e-3, device)
+        assert torch.isfinite(out).all()
+        result_host = torch.empty(shape, dtype=torch.float32).pin_memory()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev2[0].record()
+        for _ in range(steps):
+            reset()
+            di, ud, _ = to_device(host, uc_host, is_list, device, gti)
+            o = sampler.sample(S=S_STEPS, shape=shape, input=di, uc=ud, guidance_scale=GUIDANCE)
+            result_host.copy_(o, non_blocking=True)
+        ev2[1].record()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        t_e2e = parallel.max_over_ranks(ev2[0].elapsed_time(ev2[1]) * 1e-3, device)
+        images = BATCH * steps * world
+        return dict(value=images / t_dev, e2e=images / t_e2e, ms_per_step=t_dev / steps * 1e3, h2d=h2d_bytes,
+                    d2h=result_host.numel() * 4, clocks=clk.summary(), fpc=forwards_per_sample_call(S_STEPS, N_INST, mis))
 
-    # ---- end-to-end leg: host buffers in, latent back on the host, every step ------------------
-    result_host = torch.empty(shape, dtype=torch.float32).pin_memory()
-    torch.cuda.synchronize()
-    parallel.barrier()
-    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ev2[0].record()
-    for _ in range(args.steps):
-        reset()
-        di, ud, _ = to_device(host, uc_host, is_list, device, gti)
-        o = sampler.sample(S=S_STEPS, shape=shape, input=di, uc=ud, guidance_scale=GUIDANCE)
-        result_host.copy_(o, non_blocking=True)
-    ev2[1].record()
-    torch.cuda.synchronize()
-    parallel.barrier()
-    t_e2e = parallel.max_over_ranks(ev2[0].elapsed_time(ev2[1]) * 1e-3, device)
-
-    images = BATCH * args.steps * world
-    value = images / t_dev
-    e2e_value = images / t_e2e
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    head = measure(args.mis, args.steps, args.warmup)
+    # The reference's stock sampler is the Multi-instance Sampler at mis=0.36 (inference.py:59-64,176): measured
+    # in the same invocation (bounded: <= 3 steps) so that the driver sees both numbers.
+    mis_leg = None
+    if args.config == 2 and args.mis == 0 and not args.no_mis_leg:
+        mis_leg = measure(MIS_DEFAULT, max(1, min(args.steps, 3)), 1)
     if rank != 0:
         return
     roof, breakdown, launches_per_fwd = roofline_pass(model, device, peaks)
-    flop_per_image = None
-    ms_step = t_dev / args.steps * 1e3
+    value, fpc = head["value"], head["fpc"]
     line = {
         "metric": "images/sec/GPU @512^2 fp16 50-step PLMS, 8 instances", "value": value, "unit": "images/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "mis": args.mis, "global_batch": BATCH * world, "parallelism": f"dp{world}",
                    "forwards_per_call": fpc, "forward_batch": 2 * BATCH,
                    "l2_policy": "activations per forward (>1 GB at batch 8) exceed the 126 MB L2; roofline pass "
                                 "flushes L2 (256 MB write) between iterations",
                    "cuda_graph": bool(model.use_cuda_graph), "weights": "seeded random (no checkpoint offline)",
-                   "weight_broadcast_bytes": sent},
+                   "weight_broadcast_bytes": sent, "weight_broadcast_ms": bcast_ms,
+                   "weight_broadcast_wire": "fp16 matrices + fp32 vectors, one NCCL broadcast at init"},
         "per_gpu_images_per_s": value / world,
-        "clocks": clk.summary(),
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": result_host.numel() * 4},
+        "clocks": head["clocks"],
+        "e2e": {"value": head["e2e"], "unit": "images/s", "h2d_bytes_per_step": head["h2d"],
+                "d2h_bytes_per_step": head["d2h"]},
         "gpu_launches": int(launches_per_fwd * (fpc // 2) * args.steps),
         "roofline": roof,
         "breakdown": breakdown,
     }
     # per-image algorithmic work (BASELINE.md section 2): F_min(alpha=1)=1136, F_min(alpha=0)=803 GFLOP/forward/sample
-    if args.mis == 0:
+    if args.config == 2 and args.mis == 0:
         tflop = (2 * 41 * 1.136 + 2 * 10 * 0.803)
-        peak = peaks.get("bf16_tflops_sustained") or 1400.0
         line["model_roofline"] = {"tflop_per_image_fmin": tflop, "achieved_tflops": value / world * tflop,
-                                  "frac_of_sustained_peak": value / world * tflop / peak}
+                                  "frac_of_sustained_peak": value / world * tflop / peak_tf}
+    if mis_leg is not None:
+        # mis=0.36, n=8: 2*[(n+1)*(ms+1) + (S-ms)] = 406 forwards per image; all MIS steps at alpha=1 (SURVEY 8d)
+        ms = int(S_STEPS * MIS_DEFAULT)
+        n_a1 = (N_INST + 1) * (ms + 1) + (int(0.8 * S_STEPS) - ms)
+        tflop = 2 * n_a1 * 1.136 + 2 * (S_STEPS - int(0.8 * S_STEPS)) * 0.803
+        line["mis036"] = {"value": mis_leg["value"], "unit": "images/s", "per_gpu_images_per_s": mis_leg["value"] / world,
+                          "e2e": mis_leg["e2e"], "ms_per_step": mis_leg["ms_per_step"], "forwards_per_call": mis_leg["fpc"],
+                          "steps": max(1, min(args.steps, 3)), "warmup": 1, "clocks": mis_leg["clocks"],
+                          "model_roofline": {"tflop_per_image_fmin": tflop,
+                                             "achieved_tflops": mis_leg["value"] / world * tflop,
+                                             "frac_of_sustained_peak": mis_leg["value"] / world * tflop / peak_tf}}
     if not args.no_cpu_baseline:
         try:
             dt, threads = cpu_forward_seconds(2)

@@ -63,8 +63,27 @@ typedef struct {
                            zero-initialised once by the caller, then owned by the library between calls on ONE
                            stream); NULL = the process-wide default of idiff_set_gemm_workspace, if any        */
   long workspace_bytes;
+  /* LayerNorm folded across two GEMMs (attention.py:333-338 norm1/2/3, :309-310 fuser norms).  LN(x) W^T + b
+     = rstd_r (x W'^T - mean_r colsum(W')) + (W beta + b) with W' = W * gamma: the GEMM reads the
+     un-normalised residual stream, the row statistics come from the GEMM that wrote it.
+     Producer (any plain linear layer): ln_stats_out != NULL receives, per output row, the partial
+       (sum, sum of squares) of the stored row over each column slot: float2 [idiff_gemm_ln_slots(args)][M].
+     Consumer (plain or GEGLU, K <= 2560): ln_stats_in != NULL = the producer's buffer over this GEMM's A
+       rows (ln_slots_in slots, summed in slot order), w = fp16(W * gamma), ln_colsum[n] = sum_k w[n,k]
+       (fp32), bias = W beta + b, ln_eps the LayerNorm epsilon. */
+  void* ln_stats_out;
+  const void* ln_stats_in;
+  const float* ln_colsum;
+  int ln_slots_in;
+  float ln_eps;
 } idiff_gemm_args;
 int idiff_gemm(const idiff_gemm_args* args, void* stream);
+/* number of column slots a producer GEMM with these arguments writes to ln_stats_out (depends on the
+   tile plan; <= 64) */
+int idiff_gemm_ln_slots(const idiff_gemm_args* args);
+/* per-row (sum, sum of squares) of an fp16 [rows, channels] matrix as ONE slot: float2 [rows] -- the entry
+   point of the folded LayerNorm when the stream was not written by idiff_gemm (module-level calls) */
+int idiff_row_stats(const void* x, void* stats, int rows, int channels, void* stream);
 /* Stream-K scratch (fp32 partial tiles + flags) for load-balancing GEMMs whose tile count is not a
  * multiple of the SM count.  Caller-owned device memory of at least idiff_gemm_workspace_bytes().
  * Preferred: pass it per call in idiff_gemm_args.workspace (one buffer per stream -- GEMMs in flight on

@@ -25,6 +25,8 @@ class GemmArgs(C.Structure):
         ("rows_per_batch", C.c_int), ("flags", C.c_int),
         ("conv_b", C.c_int), ("conv_h", C.c_int), ("conv_w", C.c_int), ("conv_cin", C.c_int),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_long),
+        ("ln_stats_out", C.c_void_p), ("ln_stats_in", C.c_void_p), ("ln_colsum", C.c_void_p),
+        ("ln_slots_in", C.c_int), ("ln_eps", C.c_float),
     ]
 
 
@@ -51,6 +53,8 @@ SIGNATURES = {
     "idiff_last_error": (C.c_char_p, []),
     "idiff_version": (_i, []),
     "idiff_gemm": (_i, [C.POINTER(GemmArgs), _vp]),
+    "idiff_gemm_ln_slots": (_i, [C.POINTER(GemmArgs)]),
+    "idiff_row_stats": (_i, [_vp, _vp, _i, _i, _vp]),
     "idiff_gemm_workspace_bytes": (_l, []),
     "idiff_set_gemm_workspace": (_i, [_vp, _l]),
     "idiff_set_gemm_trace": (_i, [_vp]),

@@ -94,9 +94,92 @@ IDIFF_DEVICE void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t 
                : "memory");
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2: two lanes per issue slot) and the FMA-pipe exp2 ----
+IDIFF_DEVICE uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+IDIFF_DEVICE void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+IDIFF_DEVICE uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+IDIFF_DEVICE uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+IDIFF_DEVICE float max3_f(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// 2^x for two values on the FMA pipe (the MUFU pipe, 16 ex2 / clk / SM, is what bounds head_dim 40): round
+// to nearest integer with the 1.5 * 2^23 trick, degree-3 minimax polynomial of 2^r on [-0.5, 0.5]
+// (max relative error 7.5e-5, well below the fp16 rounding of P), exponent added in the integer domain.
+// Inputs are clamped at -125 (2^-125 ~ 0 next to the row maximum's 2^0..2^8).
+IDIFF_DEVICE uint64_t exp2_poly_x2(uint64_t t2) {
+  float t0, t1;
+  unpack_f32x2(t2, t0, t1);
+  t0 = fmaxf(t0, -125.0f);
+  t1 = fmaxf(t1, -125.0f);
+  const uint64_t tc = pack_f32x2(t0, t1);
+  const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);
+  const uint64_t nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+  const uint64_t z2 = add_f32x2(tc, magic);                                     // integer part in the low mantissa bits
+  const uint64_t n2 = add_f32x2(z2, nmagic);                                    // ... as a float
+  const uint64_t r2 = fma_f32x2(n2, pack_f32x2(-1.0f, -1.0f), tc);              // r = t - n in [-0.5, 0.5]
+  uint64_t p2 = fma_f32x2(r2, pack_f32x2(0.0551716685f, 0.0551716685f), pack_f32x2(0.2426111251f, 0.2426111251f));
+  p2 = fma_f32x2(p2, r2, pack_f32x2(0.6932609677f, 0.6932609677f));
+  p2 = fma_f32x2(p2, r2, pack_f32x2(0.9999280572f, 0.9999280572f));
+  float p0, p1, z0, z1;
+  unpack_f32x2(p2, p0, p1);
+  unpack_f32x2(z2, z0, z1);
+  const float e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(z0) << 23));
+  const float e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(z1) << 23));
+  return pack_f32x2(e0, e1);
+}
+
+// exponentials of one 64-key block of a row: P (fp16 pairs) and their fp32 sum.  MASK bit (u mod 8) = pair u
+// takes the FMA-pipe exp2.
+template <uint32_t MASK>
+IDIFF_DEVICE float exp_block(const uint32_t (&sv)[2][32], float c, float mc, uint32_t (&pk)[32]) {
+  uint64_t sumA = 0ull, sumB = 0ull;  // two independent packed accumulators (bit pattern of +0.0f pairs)
+  const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const uint64_t t2 = fma_f32x2(pack_f32x2(__uint_as_float(sv[hh][2 * u]), __uint_as_float(sv[hh][2 * u + 1])), c2, nmc2);
+      uint64_t e2;
+      if ((MASK >> (u & 7)) & 1u) {
+        e2 = exp2_poly_x2(t2);
+      } else {
+        float t0, t1;
+        unpack_f32x2(t2, t0, t1);
+        e2 = pack_f32x2(exp2_approx(t0), exp2_approx(t1));
+      }
+      if (u & 1) sumB = add_f32x2(sumB, e2);
+      else sumA = add_f32x2(sumA, e2);
+      float e0, e1;
+      unpack_f32x2(e2, e0, e1);
+      pk[hh * 16 + u] = pack_half2(e0, e1);
+    }
+  }
+  float sa0, sa1, sb0, sb1;
+  unpack_f32x2(sumA, sa0, sa1);
+  unpack_f32x2(sumB, sb0, sb1);
+  return (sa0 + sa1) + (sb0 + sb1);
+}
+
 // TRACE (IDIFF_ATT2_TRACE=1): one CTA records clock stamps of blocks 16..23 in shared memory and prints
 // them at exit -- a timeline of the hand-offs that costs the measured kernel nothing but a few STS.
-template <int D, bool TRACE = false>
+// POLY: bit u of the mask = pair u (mod 8) of every 8 score pairs takes the FMA-pipe exp2 instead of MUFU.
+template <int D, bool TRACE = false, uint32_t POLY = 0>
 __global__ void __launch_bounds__(THREADS, 2)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                   const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
@@ -316,11 +399,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-      for (int jj = 0; jj < 32; jj += 2) {
-        m0 = fmaxf(m0, __uint_as_float(sv[0][jj]));
-        m1 = fmaxf(m1, __uint_as_float(sv[0][jj + 1]));
-        m2 = fmaxf(m2, __uint_as_float(sv[1][jj]));
-        m3 = fmaxf(m3, __uint_as_float(sv[1][jj + 1]));
+      for (int jj = 0; jj < 32; jj += 4) {  // 3-input max: two scores per issue slot
+        m0 = max3_f(m0, __uint_as_float(sv[0][jj]), __uint_as_float(sv[0][jj + 1]));
+        m1 = max3_f(m1, __uint_as_float(sv[0][jj + 2]), __uint_as_float(sv[0][jj + 3]));
+        m2 = max3_f(m2, __uint_as_float(sv[1][jj]), __uint_as_float(sv[1][jj + 1]));
+        m3 = max3_f(m3, __uint_as_float(sv[1][jj + 2]), __uint_as_float(sv[1][jj + 3]));
       }
       const float m_blk = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       // lazy maximum: only move the reference when it grew by more than 8 in the exp2 domain
@@ -332,22 +415,15 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const float mc = m_used * c;
       if (tr) stamp(tb + 3);
       // ---- exponentials, packed to fp16 in place; row sum in fp32 ----
-      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      // Packed fp32x2 arithmetic for the exponent argument and the row sum (one issue slot per two scores);
+      // a POLY share of the pairs takes exp2 on the FMA pipe so that MUFU (8 clk per warp instruction per
+      // scheduler) and the issue slots run out together.  A ragged block (masked -inf scores) keeps MUFU
+      // (a real, warp-uniform branch: as one predicated block ptxas evaluated both variants and selected).
       uint32_t pk[32];
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-        for (int u = 0; u < 16; u += 2) {
-          const float e0 = exp2_approx(fmaf(__uint_as_float(sv[hh][2 * u]), c, -mc));
-          const float e1 = exp2_approx(fmaf(__uint_as_float(sv[hh][2 * u + 1]), c, -mc));
-          const float e2 = exp2_approx(fmaf(__uint_as_float(sv[hh][2 * u + 2]), c, -mc));
-          const float e3 = exp2_approx(fmaf(__uint_as_float(sv[hh][2 * u + 3]), c, -mc));
-          sum0 += e0; sum1 += e1; sum2 += e2; sum3 += e3;
-          pk[hh * 16 + u] = pack_half2(e0, e1);
-          pk[hh * 16 + u + 1] = pack_half2(e2, e3);
-        }
-      }
-      l = fmaf(l, alpha, (sum0 + sum1) + (sum2 + sum3));
+      float blk_sum;
+      if (POLY != 0 && nv == BKV) blk_sum = exp_block<POLY>(sv, c, mc, pk);
+      else blk_sum = exp_block<0u>(sv, c, mc, pk);
+      l = fmaf(l, alpha, blk_sum);
       if (tr) stamp(tb + 4);
       // ---- P buffer free (P.V(j-1) done); rare O rescale; P -> shared memory ----
       if (j > 0) {
@@ -466,13 +542,24 @@ int attention_v2_d40(const idiff_attn_args* a, cudaStream_t stream) {
   p.out = reinterpret_cast<__half*>(a->out);
   p.out_ld = a->out_ld;
   static const bool trace = getenv("IDIFF_ATT2_TRACE") != nullptr;
-  auto kern = trace ? attention2_kernel<D, true> : attention2_kernel<D, false>;
+  // share of the exponentials taken on the FMA pipe: pairs per 8 (IDIFF_ATT2_POLY=0..4, tuning knob)
+  static const int poly = []() {
+    const char* e = getenv("IDIFF_ATT2_POLY");
+    const int v = e ? atoi(e) : 3;
+    return (v >= 0 && v <= 4) ? v : 3;
+  }();
+  auto kern = trace ? attention2_kernel<D, true, 0u>
+              : poly == 0 ? attention2_kernel<D, false, 0u>
+              : poly == 1 ? attention2_kernel<D, false, 0x10u>
+              : poly == 2 ? attention2_kernel<D, false, 0x22u>
+              : poly == 3 ? attention2_kernel<D, false, 0x4Au>
+                          : attention2_kernel<D, false, 0xAAu>;
   const int smem_bytes = C::SMEM_BYTES + (trace ? C::TRACE_BYTES : 0);
   static bool attr_set = false;
   if (!attr_set) {
     IDIFF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     IDIFF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
+    attr_set = true;  // (`kern` is fixed for the life of the process: both knobs are read once)
   }
   dim3 grid((a->nq + 2 * BQ - 1) / (2 * BQ), a->heads, a->batch);
   IDIFF_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), smem_bytes, stream, tmQ, tmK0, tmV0, tmK1, tmV1, p));

@@ -37,8 +37,13 @@ namespace v2 {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int THREADS = 384;  // 3 warpgroups: {TMA, UMMA, 2 idle} + 2 x 4 epilogue warps
-constexpr int EPI_WARPS = 8;
+// Warpgroup 0 = {TMA, UMMA, 2 idle warps}; then EW epilogue warps (EW / 4 per TMEM lane quarter).
+// EW = 8 (two column halves) is the long-K configuration: the epilogue hides behind the next tile's
+// mainloop and the warps may use 224 registers.  EW = 16 (four column parts, 104 registers) is for the
+// short-K layers, which are bound by the epilogue's serial latency chain per 16-column chunk (TMEM load
+// -> wait -> table / residual LDS -> STS -> proxy fence -> TMA store, ~1000 clk): four epilogue warps per
+// scheduler instead of two hide it, and each warp owns half as many chunks per tile.
+constexpr int MAX_EPI_WARPS = 16;
 constexpr int CHUNK = 16;  // accumulator columns per tcgen05.ld
 constexpr int EPI_TAB_PB = 4;  // batches a conv tile may straddle and still use the smem epilogue table
 
@@ -59,6 +64,12 @@ struct Params {
   float* ws;    // [G][BN/CHUNK][128][CHUNK] fp32 partial tiles
   int* sflags;  // [G][EPI_WARPS] publish flags (fixed location, self-resetting)
   unsigned long long* trace;  // optional [G][8] %globaltimer stamps (idiff_set_gemm_trace), else null
+  // LayerNorm folded across GEMMs (header: ln_* fields)
+  float2* ln_out;        // producer: [n_tiles * PARTS][M] partial (sum, sumsq) of the output rows
+  const float2* ln_in;   // consumer: [ln_slots][M] partials of the A rows
+  const float* ln_s;     // consumer: [N] column sums of the gamma-folded fp16 weights
+  int ln_slots;
+  float ln_eps;
 };
 
 // TMA_EPI: the epilogue moves the residual in and the result out through shared memory with
@@ -66,14 +77,19 @@ struct Params {
 // 16-byte global access per thread and row (which costs an L1 transaction per access: measured
 // ~0.7 us per chunk, tools/trace_gemm.py).  The staging buffer takes smem from the operand ring,
 // so it is used for the short-K layers (epilogue-bound); long-K convolutions keep the deep ring.
-template <int BN, bool TMA_EPI>
+template <int BN, bool TMA_EPI, int EW = 8>
 struct Cfg {
+  static constexpr int THREADS = 128 + EW * 32;
+  static constexpr int PARTS = EW / 4;            // column parts of a tile (one epilogue warp per quarter and part)
+  static constexpr int NCHT = BN / CHUNK;         // 16-column accumulator chunks of a tile
+  static constexpr int NCH_MAX = (NCHT + PARTS - 1) / PARTS;  // ... owned by one warp, at most
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int BOX_BYTES = 32 * CHUNK * 2;                       // 1 KiB
-  static constexpr int STG_BYTES = TMA_EPI ? EPI_WARPS * (BN / 2 / CHUNK) * BOX_BYTES : 0;
+  static constexpr int STG_BYTES = TMA_EPI ? 4 * NCHT * BOX_BYTES : 0;  // [quarter][chunk] boxes
   static constexpr int TAB_BYTES = 2 * EPI_TAB_PB * BN * 4;
-  static constexpr int FIXED = 1024 + 256 + TAB_BYTES + STG_BYTES;
+  static constexpr int BAR_BYTES = 512;  // 2*STAGES + 4 + MAX_EPI_WARPS mbarriers (<= 32 x 8 B) + the TMEM base slot
+  static constexpr int FIXED = 1024 + BAR_BYTES + TAB_BYTES + STG_BYTES;
   static constexpr int STAGES_FIT = (227 * 1024 - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;
@@ -152,13 +168,14 @@ constexpr int MODE_PLAIN = 0;  // bias / row-add table, optional SiLU, optional 
 constexpr int MODE_GEGLU = 1;  // (value + b) * gelu(gate + b), fp16 out with N/2 columns
 constexpr int MODE_NCHW = 2;   // fp32 (B, N, HW) output (the final conv -> eps)
 
-template <int BN, int MODE, bool TMA_EPI>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int BN, int MODE, bool TMA_EPI, int EW, bool REALLOC = true>
+__global__ void __launch_bounds__(128 + EW * 32, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
              const Params p) {
-  using C = Cfg<BN, TMA_EPI>;
+  using C = Cfg<BN, TMA_EPI, EW>;
   constexpr int STAGES = C::STAGES;
+  constexpr int EPI_WARPS = EW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -170,9 +187,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
   uint64_t* res_bar = bars + 2 * STAGES + 4;     // [EPI_WARPS] residual boxes landed (TMA_EPI)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + EPI_WARPS);
-  float* s_epi = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES + 256);  // [2][EPI_TAB_PB][BN]
-  uint8_t* s_stage = smem + STAGES * C::STAGE_BYTES + 256 + C::TAB_BYTES;          // [EPI_WARPS][NCH][1 KiB]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + MAX_EPI_WARPS);
+  float* s_epi = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES + C::BAR_BYTES);  // [2][EPI_TAB_PB][BN]
+  uint8_t* s_stage = smem + STAGES * C::STAGE_BYTES + C::BAR_BYTES + C::TAB_BYTES;          // [quarter][NCHT][1 KiB]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -234,7 +251,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // Warpgroup 0 = {TMA, UMMA, 2 idle warps} gives registers to the two epilogue warpgroups
   // (setmaxnreg at the head of each role branch: 56*128 + 224*256 = the CTA's 168*384 allocation).
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
+  // launch allocation -> after the split:  EW 8: 384 x 168 = 128 x 56 + 256 x 224;  EW 12: 512 x 128 = 128 x 56 +
+  // 384 x 152;  EW 16: 640 x 96 >= 128 x 48 + 512 x 104
+  if constexpr (!REALLOC) {  // diagnostic variant: every warp keeps its launch allocation
+  } else if constexpr (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;\n");
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -297,24 +318,34 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     __syncwarp();
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n");
+    if constexpr (!REALLOC) {
+    } else if constexpr (EW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n");
+    else if constexpr (EW == 12) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;\n");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n");
     // ===================== epilogue (warps 4..11) =====================
     const int ew = warp - 4;       // 0..7
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int half = ew >> 2;      // which half of the tile's columns
+    const int part = ew >> 2;      // which column part of the tile (EW / 4 parts)
     const int r = quarter * 32 + lane;
     constexpr bool geglu = (MODE == MODE_GEGLU);
     constexpr bool nchw = (MODE == MODE_NCHW);
     const bool do_silu = (p.flags & IDIFF_EPI_SILU) != 0;
     const bool do_gelu = (p.flags & IDIFF_EPI_GELU) != 0;
     const int n_out_total = geglu ? p.N / 2 : p.N;
-    constexpr int NCH = BN / 2 / CHUNK;  // accumulator chunks owned by this warp
-    // Accumulator column of chunk `ch` of this warp.  Plain: a contiguous half of the tile.
-    // GEGLU: value columns [half*BN/4, +BN/4) followed by their gate columns (BN/2 further on), so
+    constexpr int NCH = C::NCH_MAX;  // accumulator chunks owned by this warp, at most
+    constexpr int PARTS = C::PARTS;
+    // This warp's chunks.  Plain: the contiguous run [cb, ce) of the tile's NCHT chunks (parts differ by
+    // one chunk when PARTS does not divide NCHT, e.g. BN = 160 over four parts: 2, 3, 2, 3).
+    // GEGLU: value chunks [cb, ce) of the NCHT / 2 value chunks followed by their gate chunks (BN/2
+    // columns further on), so
     // that a warp publishes exactly the columns its owner counterpart consumes.
+    constexpr int NOUT_CH = geglu ? C::NCHT / 2 : C::NCHT;  // output chunks of a tile
+    const int cb = part * NOUT_CH / PARTS, ce = (part + 1) * NOUT_CH / PARTS;
+    const int nv = ce - cb;                 // output chunks of this warp
+    const int nch = geglu ? 2 * nv : nv;    // accumulator chunks of this warp
     auto chunk_col = [&](int ch) -> int {
-      if (!geglu) return half * (BN / 2) + ch * CHUNK;
-      return (ch < NCH / 2) ? (half * (BN / 4) + ch * CHUNK) : (BN / 2 + half * (BN / 4) + (ch - NCH / 2) * CHUNK);
+      if (!geglu) return (cb + ch) * CHUNK;
+      return (ch < nv) ? (cb + ch) * CHUNK : (BN / 2 + (cb + ch - nv) * CHUNK);
     };
 
     WorkIter it(p, cta);
@@ -362,7 +393,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint4 resv[TMA_EPI ? 1 : NCH][2];
       const bool has_res = owner && (TMA_EPI || row_ok) && p.residual != nullptr && !geglu;
       // staging boxes of this warp: box ch holds rows [32*quarter, +32) x 16 output columns
-      uint8_t* wstage = s_stage + (TMA_EPI ? ew * (NCH * C::BOX_BYTES) : 0);
+      uint8_t* wstage = s_stage + (TMA_EPI ? (quarter * C::NCHT + cb) * C::BOX_BYTES : 0);
       // tile-local coordinates of this warp's first row, for the output / residual tensor maps
       int tc1 = 0, tc2 = 0, tc3 = 0;
       if (TMA_EPI && owner) {
@@ -383,12 +414,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           int nbox = 0;
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch)
-            if (out_col_base + half * (BN / 2) + ch * CHUNK < n_out_total) ++nbox;
+            if (ch < nv && out_col_base + chunk_col(ch) < n_out_total) ++nbox;
           mbar_expect_tx(&res_bar[ew], nbox * C::BOX_BYTES);
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch) {
-            const int col = out_col_base + half * (BN / 2) + ch * CHUNK;
-            if (col < n_out_total) {
+            const int col = out_col_base + chunk_col(ch);
+            if (ch < nv && col < n_out_total) {
               if (p.conv) tma_load_4d(wstage + ch * C::BOX_BYTES, &tmR, &res_bar[ew], col, tc1, tc2, tc3);
               else tma_load_2d(wstage + ch * C::BOX_BYTES, &tmR, &res_bar[ew], col, tc1);
             }
@@ -399,8 +430,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const __half* res_row = p.residual + out_row * p.ldr + out_col_base;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
-          const int c0 = half * (BN / 2) + ch * CHUNK;
-          if (out_col_base + c0 < n_out_total) {
+          const int c0 = chunk_col(ch);
+          if (ch < nv && out_col_base + c0 < n_out_total) {
             resv[ch][0] = *reinterpret_cast<const uint4*>(res_row + c0);
             if (out_col_base + c0 + 8 < n_out_total) resv[ch][1] = *reinterpret_cast<const uint4*>(res_row + c0 + 8);
           }
@@ -424,10 +455,29 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (tab_rowadd && b0 + pb < p.Bn) val += __half2float(p.rowadd[(long)(b0 + pb) * p.ldra + col]);
           }
           tab[idx] = val;
+          if (p.ln_in) tab[BN + idx] = (col < p.N) ? __ldg(p.ln_s + col) : 0.f;  // row 1: sum_k W'[col, k]
         }
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_WARPS * 32) : "memory");
       }
       const float* tab_row = tab + ((tab_rowadd && p.conv) ? (r / (p.PW * p.PH)) * BN : 0);
+      // LayerNorm fold, consumer side: this row's mean / rstd from the producer GEMM's partial sums, added
+      // in slot order (deterministic).  y = rstd * (x . W'^T - mean * colsum(W')) + (W beta + b).
+      float ln_nmean = 0.f, ln_rstd = 1.f;
+      if (TMA_EPI && p.ln_in != nullptr && owner) {
+        float a = 0.f, q = 0.f;
+        if (row_ok) {
+          for (int sl = 0; sl < p.ln_slots; ++sl) {
+            const float2 v = __ldcg(p.ln_in + (long)sl * p.M + out_row);
+            a += v.x;
+            q += v.y;
+          }
+        }
+        const float inv_k = 1.0f / (float)p.K;
+        const float mean = a * inv_k;
+        ln_rstd = rsqrtf(fmaxf(q * inv_k - mean * mean, 0.f) + p.ln_eps);
+        ln_nmean = -mean;
+      }
+      float ln_ps = 0.f, ln_pq = 0.f;  // producer side: partial (sum, sumsq) of this warp's output columns
       mbar_wait(&tmem_full[acc], (sc >> 1) & 1);
       if (sc == 0 && threadIdx.x == 128) stamp(3);
       tc_fence_after();
@@ -437,7 +487,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // ---- publish the fp32 partial of this warp's region: ws[cta][chunk][row][CHUNK] ----
         float* wsb = p.ws + (long)cta * (BN / CHUNK) * 128 * CHUNK;
 #pragma unroll 1
-        for (int ch = 0; ch < NCH; ++ch) {
+        for (int ch = 0; ch < nch; ++ch) {
           const int c0 = chunk_col(ch);
           uint32_t v[CHUNK];
           tmem_ld_32x32b_x16(trow + c0, v);
@@ -479,7 +529,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           constexpr int FB = 4;
           const long fstride = (long)(BN / CHUNK) * 128 * CHUNK;
 #pragma unroll 1
-          for (int ch = 0; ch < NCH; ++ch) {
+          for (int ch = 0; ch < nch; ++ch) {
             const int c0 = chunk_col(ch);
             uint32_t av[CHUNK];
             tmem_ld_32x32b_x16(trow + c0, av);
@@ -535,8 +585,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           // Compact rolled loop (one 16-column chunk per trip, ~150 instructions, explicit
           // ld/st.shared): the unrolled variant below was instruction-fetch bound for short-K layers
           // (26 % stall_no_inst, generic LD for shared operands; profiles/).
-          constexpr int NVT = geglu ? NCH / 2 : NCH;
-          const int cbase = geglu ? half * (BN / 4) : half * (BN / 2);
+          const int cbase = cb * CHUNK;
           const uint32_t tab_s = smem_u32(tab_row);
           const uint32_t box_s = smem_u32(wstage) + lane * 32;
           const uint32_t sw16 = ((lane >> 2) & 1) << 4;
@@ -545,7 +594,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                          : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(a));
           };
 #pragma unroll 1
-          for (int ch = 0; ch < NVT; ++ch) {
+          for (int ch = 0; ch < nv; ++ch) {
             const int c0 = cbase + ch * CHUNK;
             const int out_c = out_col_base + c0;
             if (out_c >= n_out_total) break;  // warp-uniform
@@ -562,6 +611,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 x[j] = __uint_as_float(v[j]);
                 gx[j] = __uint_as_float(g[j]);
               }
+              if (p.ln_in != nullptr) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  float sv[4], sg[4];
+                  lds4(tab_s + (BN + c0 + 4 * q) * 4, sv);
+                  lds4(tab_s + (BN + BN / 2 + c0 + 4 * q) * 4, sg);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    x[4 * q + j] = ln_rstd * fmaf(ln_nmean, sv[j], x[4 * q + j]);
+                    gx[4 * q + j] = ln_rstd * fmaf(ln_nmean, sg[j], gx[4 * q + j]);
+                  }
+                }
+              }
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 float bv[4], bg[4];
@@ -574,6 +636,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < CHUNK; ++j) x[j] = __uint_as_float(v[j]);
+              if (p.ln_in != nullptr) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  float sv[4];
+                  lds4(tab_s + (BN + c0 + 4 * q) * 4, sv);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) x[4 * q + j] = ln_rstd * fmaf(ln_nmean, sv[j], x[4 * q + j]);
+                }
+              }
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 float bv[4];
@@ -614,6 +685,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   y[2 * j + 1] = fmaf(gate, y[2 * j + 1], f.y);
                 }
               }
+              if (p.ln_out != nullptr && out_c + 8 * q < n_out_total) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  ln_ps += y[j];
+                  ln_pq = fmaf(y[j], y[j], ln_pq);
+                }
+              }
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(slot), "r"(pack_half2(y[0], y[1])),
                            "r"(pack_half2(y[2], y[3])), "r"(pack_half2(y[4], y[5])), "r"(pack_half2(y[6], y[7]))
                            : "memory");
@@ -630,8 +708,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // before one wait, all results are staged before one proxy fence / warp sync, and the
         // group's TMA stores go out together.  (Chunk-at-a-time was a ~1200-cycle serial dependency
         // chain per 16 columns with only two warps per scheduler to hide it: tools/trace_gemm.py.)
-        constexpr int GROUP = 4;
-        constexpr int NV = geglu ? NCH / 2 : NCH;  // output chunks of this warp
+        constexpr int GROUP = (EW == 16) ? 2 : 4;  // 104-register epilogue warps hold two chunks at a time
+        constexpr int NV = (NOUT_CH + PARTS - 1) / PARTS;  // output chunks of this warp, at most
 #pragma unroll
         for (int g0 = 0; g0 < NV; g0 += GROUP) {
           uint32_t xv[GROUP][CHUNK];
@@ -643,7 +721,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int i = 0; i < GROUP; ++i) {
             const int ch = g0 + i;
-            live[i] = (ch < NV) && (out_col_base + chunk_col(ch < NV ? ch : 0) < n_out_total);
+            live[i] = (ch < nv) && (out_col_base + chunk_col(ch < nv ? ch : 0) < n_out_total);
             if (live[i]) {
               const int c0 = chunk_col(ch);
               tmem_ld_32x32b_x16(trow + c0, xv[i]);
@@ -764,6 +842,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                       y[2 * j + 1] = fmaf(gate, y[2 * j + 1], f.y);
                     }
                   }
+                  if (p.ln_out != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      ln_ps += y[j];
+                      ln_pq = fmaf(y[j], y[j], ln_pq);
+                    }
+                  }
                   *(reinterpret_cast<uint4*>(o_row + c0) + q) =
                       make_uint4(pack_half2(y[0], y[1]), pack_half2(y[2], y[3]), pack_half2(y[4], y[5]),
                                  pack_half2(y[6], y[7]));
@@ -790,6 +875,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         }  // direct / grouped epilogue
         if (TMA_EPI && lane == 0) tma_store_commit();
+        // LayerNorm fold, producer side: this warp's partial row statistics, slot = (n tile, column part);
+        // consecutive lanes own consecutive rows -> one coalesced 256-byte store per warp
+        if (p.ln_out != nullptr && row_ok)
+          __stcg(p.ln_out + (long)((sg.tile % p.n_tiles) * PARTS + part) * p.M + out_row, make_float2(ln_ps, ln_pq));
         if (sc == 0 && threadIdx.x == 128) stamp(5);
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
@@ -840,9 +929,9 @@ static void choose_patch(int H, int W, int* PW, int* PH, int* PB) {
   *PB = 128 / (pw * ph);
 }
 
-template <int BN, int MODE, bool TMA_EPI>
+template <int BN, int MODE, bool TMA_EPI, int EW = 8, bool REALLOC = true>
 static int launch(const idiff_gemm_args* a, cudaStream_t stream, bool want_sk) {
-  using C = Cfg<BN, TMA_EPI>;
+  using C = Cfg<BN, TMA_EPI, EW>;
   Params p;
   memset(&p, 0, sizeof(p));
   p.M = a->M;
@@ -860,6 +949,11 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream, bool want_sk) {
   p.flags = a->flags;
   p.gate = a->gate;
   p.trace = g_trace;
+  p.ln_out = reinterpret_cast<float2*>(a->ln_stats_out);
+  p.ln_in = reinterpret_cast<const float2*>(a->ln_stats_in);
+  p.ln_s = a->ln_colsum;
+  p.ln_slots = a->ln_slots_in;
+  p.ln_eps = a->ln_eps;
 
   CUtensorMap tmA, tmB;
   int m_tiles;
@@ -949,11 +1043,11 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream, bool want_sk) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MODE, TMA_EPI>,
+    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MODE, TMA_EPI, EW, REALLOC>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  IDIFF_CHECK_CUDA(launch_pdl(gemm2_kernel<BN, MODE, TMA_EPI>, dim3(p.G), dim3(THREADS), C::SMEM_BYTES, stream, tmA, tmB, tmO, tmR, p));
+  IDIFF_CHECK_CUDA(launch_pdl(gemm2_kernel<BN, MODE, TMA_EPI, EW, REALLOC>, dim3(p.G), dim3(C::THREADS), C::SMEM_BYTES, stream, tmA, tmB, tmO, tmR, p));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1036,23 +1130,68 @@ static Plan plan_gemm(const idiff_gemm_args* a, int fixed_bn) {  // fixed_bn: 0 
   return best;
 }
 
-// One instantiation per (tile width, epilogue mode): the epilogue is fully unrolled over its
-// column chunks, so each kernel carries only its own mode's code (an all-modes kernel was ~140 KB
-// of SASS and stalled on instruction fetch: 26 % stall_no_inst, profiles/).
-int gemm_v2(const idiff_gemm_args* a, cudaStream_t stream) {
+struct Resolved {
+  int bn, mode, ew;
+  bool tma_epi, sk;
+};
+static Resolved resolve(const idiff_gemm_args* a) {
+  // epilogue warps of the short-K layers: IDIFF_GEMM_EW = 8 (default until the wider ones are verified) / 12 / 16
+  static const int ew_short = []() {
+    const char* e = getenv("IDIFF_GEMM_EW");
+    const int v = e ? atoi(e) : 8;
+    return (v == 12 || v == 13 || v == 16 || v == 17) ? v : 8;  // 13 / 17: 12 / 16 warps without setmaxnreg (diagnostic)
+  }();
+  Resolved r;
   // GEGLU: one 256-column accumulator tile = 128 value columns + their 128 gates (packing.py)
-  if (a->flags & IDIFF_EPI_GEGLU) return launch<256, MODE_GEGLU, true>(a, stream, plan_gemm(a, 256).sk);
-  if (a->flags & IDIFF_OUT_F32_NCHW) return launch<128, MODE_NCHW, false>(a, stream, plan_gemm(a, 128).sk);
+  if (a->flags & IDIFF_EPI_GEGLU) {
+    r = {256, MODE_GEGLU, ew_short, true, plan_gemm(a, 256).sk};
+    return r;
+  }
+  if (a->flags & IDIFF_OUT_F32_NCHW) {
+    r = {128, MODE_NCHW, 8, false, plan_gemm(a, 128).sk};
+    return r;
+  }
   // short K: the epilogue dominates -> TMA-staged epilogue (shallower operand ring);
   // long K (3x3 convolutions): deep operand ring, direct epilogue hidden behind the next mainloop
   const bool tma_epi = ((a->K + BK - 1) / BK) <= kTmaEpiMaxKB;
   const Plan pl = plan_gemm(a, false);
-  switch (pl.bn) {
-    case 256: return tma_epi ? launch<256, MODE_PLAIN, true>(a, stream, pl.sk) : launch<256, MODE_PLAIN, false>(a, stream, pl.sk);
-    case 192: return tma_epi ? launch<192, MODE_PLAIN, true>(a, stream, pl.sk) : launch<192, MODE_PLAIN, false>(a, stream, pl.sk);
-    case 160: return tma_epi ? launch<160, MODE_PLAIN, true>(a, stream, pl.sk) : launch<160, MODE_PLAIN, false>(a, stream, pl.sk);
-    default: return tma_epi ? launch<128, MODE_PLAIN, true>(a, stream, pl.sk) : launch<128, MODE_PLAIN, false>(a, stream, pl.sk);
+  r = {pl.bn, MODE_PLAIN, tma_epi ? ew_short : 8, tma_epi, pl.sk};
+  return r;
+}
+
+template <int BN>
+static int launch_plain(const Resolved& r, const idiff_gemm_args* a, cudaStream_t stream) {
+  if (!r.tma_epi) return launch<BN, MODE_PLAIN, false, 8>(a, stream, r.sk);
+  if (r.ew == 16) return launch<BN, MODE_PLAIN, true, 16>(a, stream, r.sk);
+  if (r.ew == 12) return launch<BN, MODE_PLAIN, true, 12>(a, stream, r.sk);
+  if (r.ew == 13) return launch<BN, MODE_PLAIN, true, 12, false>(a, stream, r.sk);
+  if (r.ew == 17) return launch<BN, MODE_PLAIN, true, 16, false>(a, stream, r.sk);
+  return launch<BN, MODE_PLAIN, true, 8>(a, stream, r.sk);
+}
+
+// One instantiation per (tile width, epilogue mode, epilogue warps): each kernel carries only its own
+// mode's code (an all-modes kernel was ~140 KB of SASS and stalled on instruction fetch: 26 %
+// stall_no_inst, profiles/).
+int gemm_v2(const idiff_gemm_args* a, cudaStream_t stream) {
+  const Resolved r = resolve(a);
+  if (r.mode == MODE_GEGLU) {
+    return (r.ew == 16 || r.ew == 17) ? launch<256, MODE_GEGLU, true, 16>(a, stream, r.sk)
+           : (r.ew == 12 || r.ew == 13) ? launch<256, MODE_GEGLU, true, 12>(a, stream, r.sk)
+                                        : launch<256, MODE_GEGLU, true, 8>(a, stream, r.sk);
   }
+  if (r.mode == MODE_NCHW) return launch<128, MODE_NCHW, false, 8>(a, stream, r.sk);
+  switch (r.bn) {
+    case 256: return launch_plain<256>(r, a, stream);
+    case 192: return launch_plain<192>(r, a, stream);
+    case 160: return launch_plain<160>(r, a, stream);
+    default: return launch_plain<128>(r, a, stream);
+  }
+}
+
+// slots of the LayerNorm partial statistics a producer GEMM with these arguments writes per row
+int ln_slots_of(const idiff_gemm_args* a) {
+  const Resolved r = resolve(a);
+  return ((a->N + r.bn - 1) / r.bn) * ((r.ew == 13 ? 12 : r.ew == 17 ? 16 : r.ew) / 4);
 }
 
 }  // namespace v2
@@ -1082,7 +1221,23 @@ extern "C" int idiff_gemm(const idiff_gemm_args* a, void* stream) {
   if (a->workspace) {
     IDIFF_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "idiff_gemm: workspace must be 256B aligned");
   }
+  if (a->ln_stats_in) {
+    IDIFF_REQUIRE(a->ln_colsum && a->ln_slots_in > 0 && a->ln_slots_in <= 64, "idiff_gemm: LayerNorm fold needs ln_colsum and 1..64 slots");
+    IDIFF_REQUIRE(a->conv_h == 0 && !nchw && !a->rowadd, "idiff_gemm: LayerNorm fold applies to plain / GEGLU linear layers");
+    IDIFF_REQUIRE((a->K + 63) / 64 <= 40, "idiff_gemm: LayerNorm fold needs K <= 2560 (K=%d)", a->K);
+    IDIFF_REQUIRE((reinterpret_cast<uintptr_t>(a->ln_stats_in) & 7) == 0, "idiff_gemm: ln_stats_in must be 8B aligned");
+  }
+  if (a->ln_stats_out) {
+    IDIFF_REQUIRE(a->conv_h == 0 && !nchw && !geglu, "idiff_gemm: row statistics are produced by plain linear layers");
+    IDIFF_REQUIRE((reinterpret_cast<uintptr_t>(a->ln_stats_out) & 7) == 0, "idiff_gemm: ln_stats_out must be 8B aligned");
+  }
   return v2::gemm_v2(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int idiff_gemm_ln_slots(const idiff_gemm_args* a) {
+  using namespace idiff;
+  IDIFF_REQUIRE(a && a->M > 0 && a->N > 0 && a->K > 0, "idiff_gemm_ln_slots: bad arguments");
+  return v2::ln_slots_of(a);
 }
 
 extern "C" int idiff_set_gemm_workspace(void* ptr, long bytes) {

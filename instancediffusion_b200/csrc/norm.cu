@@ -461,7 +461,46 @@ layernorm_generic_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, con
   }
 }
 
+// Row statistics for the folded LayerNorm (include/idiff_b200.h idiff_gemm_args.ln_*): one warp per row,
+// (sum, sum of squares) in fp32, fixed order.  Only used where the stream was not written by idiff_gemm
+// (module-level entry points); inside the UNet the producing GEMM's epilogue writes the statistics.
+__global__ void __launch_bounds__(256)
+row_stats_kernel(const uint4* __restrict__ x, float2* __restrict__ stats, int rows, int CV) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float a = 0.f, q = 0.f;
+  for (int cv = lane; cv < CV; cv += 32) {
+    float f[8];
+    unpack8(x[(long)row * CV + cv], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a += f[j];
+      q = fmaf(f[j], f[j], q);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) stats[row] = make_float2(a, q);
+}
+
 }  // namespace idiff
+
+extern "C" int idiff_row_stats(const void* x, void* stats, int rows, int channels, void* stream) {
+  using namespace idiff;
+  IDIFF_REQUIRE(x && stats && rows > 0, "idiff_row_stats: bad arguments");
+  IDIFF_REQUIRE(channels % 8 == 0 && channels > 0, "idiff_row_stats: C=%d must be a multiple of 8", channels);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  IDIFF_CHECK_CUDA(launch_pdl(row_stats_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, reinterpret_cast<const uint4*>(x),
+                              reinterpret_cast<float2*>(stats), rows, channels / 8));
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 // geometry shared by the GroupNorm launches and the workspace-size query
 static void gn_geometry(int batch, int hw, int channels, int* k, int* ppb, int* chunks) {

@@ -41,6 +41,14 @@ class PackedModule(nn.Module):
     def _pack(self):  # pragma: no cover - overridden
         return {}
 
+    def lazy(self, name: str, make):
+        """Pack entries only some call paths need (e.g. the un-folded QKV weights of the module-level API)."""
+        p = self.pk()
+        if name not in p:
+            with torch.no_grad():
+                p[name] = make()
+        return p[name]
+
 
 def dev_of(p: torch.Tensor) -> torch.device:
     if not p.is_cuda:

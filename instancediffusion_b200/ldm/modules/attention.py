@@ -5,6 +5,13 @@ libidiff_b200.so (tcgen05 GEMM + flash attention + LayerNorm/GroupNorm kernels).
 Internal convention: token-major fp16 activations `[B*N, C]` (== NHWC), carried between the
 `_fwd` methods without any NCHW<->(B,HW,C) rearrange (attention.py:369,376 disappear).
 The public `forward` methods keep the reference layouts and are used for module-level parity.
+
+LayerNorm never runs as its own pass on the visual stream: LN(x) W^T + b = rstd (x W'^T - mean colsum(W'))
++ (W beta + b) with W' = W * gamma, so the GEMM that consumes a LayerNorm reads the un-normalised stream
+with gamma-folded weights and applies (mean, rstd) per row in its epilogue; the row statistics are partial
+sums written by the epilogue of the GEMM that produced the stream (ops.RowStats, idiff_gemm_args.ln_*).
+The `ln=` arguments below carry (RowStats, ops.LnFold); parents own the fold because the LayerNorm
+parameters live in the parent block (attention.py:294-295, 320-322).
 """
 from __future__ import annotations
 
@@ -45,9 +52,15 @@ class GEGLU(PackedModule):
         wp, bp = pack_geglu(w16(self.proj.weight), f32(self.proj.bias))
         return {"w": wp, "b": bp}
 
-    def _fwd(self, x16: torch.Tensor) -> torch.Tensor:
+    def _fwd(self, x16: torch.Tensor, ln=None) -> torch.Tensor:
+        if ln is not None:  # (RowStats of x16, LnFold of this projection): x16 is the un-normalised stream
+            st, f = ln
+            return ops.gemm(x16, f.w, f.bias, geglu=True, ln=(st, f.colsum, f.eps))
         p = self.pk()
         return ops.gemm(x16, p["w"], p["b"], geglu=True)
+
+    def fold(self, norm: nn.LayerNorm) -> "ops.LnFold":
+        return ops.fold_layernorm(self.proj.weight, self.proj.bias, norm.weight, norm.bias, norm.eps, pack=pack_geglu)
 
     def forward(self, x):
         x16, B, N = to_tokens(x)
@@ -68,11 +81,12 @@ class FeedForward(PackedModule):
     def _pack(self):
         return {"w2": w16(self.net[2].weight), "b2": f32(self.net[2].bias)}
 
-    def _fwd(self, x16, residual=None, gate=1.0, out=None):
-        """x16: LayerNorm-ed input.  Returns residual + gate * FF(x16) (or FF(x16) without residual)."""
+    def _fwd(self, x16, residual=None, gate=1.0, out=None, ln=None, want_stats=False):
+        """x16: LayerNorm-ed input (or, with ln=(RowStats, LnFold), the stream itself).  Returns residual +
+        gate * FF(x16) (or FF(x16) without residual); with want_stats also the RowStats of the result."""
         p = self.pk()
-        h = self.net[0]._fwd(x16)
-        return ops.gemm(h, p["w2"], p["b2"], residual=residual, gate=gate, out=out)
+        h = self.net[0]._fwd(x16, ln=ln)
+        return ops.gemm(h, p["w2"], p["b2"], residual=residual, gate=gate, out=out, want_stats=want_stats)
 
     def forward(self, x):
         x16, B, N = to_tokens(x)
@@ -100,23 +114,29 @@ class CrossAttention(PackedModule):
 
     def _pack(self):
         return {
-            "wq": w16(self.to_q.weight),
             "wkv": torch.cat([w16(self.to_k.weight), w16(self.to_v.weight)], 0).contiguous(),
             "wo": w16(self.to_out[0].weight),
             "bo": f32(self.to_out[0].bias),
         }
 
+    def fold_q(self, norm: nn.LayerNorm) -> "ops.LnFold":
+        return ops.fold_layernorm(self.to_q.weight, None, norm.weight, norm.bias, norm.eps)
+
     def project_kv(self, ctx16: torch.Tensor) -> torch.Tensor:
         """ctx16 fp16 [B*M, key_dim] -> [B*M, 2*inner] = [K | V]."""
         return ops.gemm(ctx16, self.pk()["wkv"])
 
-    def _fwd(self, x16, kv, B, N, M, residual=None, out=None):
+    def _fwd(self, x16, kv, B, N, M, residual=None, out=None, ln=None, want_stats=False):
         p = self.pk()
         C = self.heads * self.dim_head
-        q = ops.gemm(x16, p["wq"])
+        if ln is not None:
+            st, f = ln
+            q = ops.gemm(x16, f.w, f.bias, ln=(st, f.colsum, f.eps))
+        else:
+            q = ops.gemm(x16, self.lazy("wq", lambda: w16(self.to_q.weight)))
         a = ops.attention(q, kv[:, :C], kv[:, C:2 * C], batch=B, heads=self.heads, head_dim=self.dim_head,
                           nq=N, n0=M, scale=self.scale)
-        return ops.gemm(a, p["wo"], p["bo"], residual=residual, out=out)
+        return ops.gemm(a, p["wo"], p["bo"], residual=residual, out=out, want_stats=want_stats)
 
     def forward(self, x, key, value, mask=None):
         if mask is not None:
@@ -145,29 +165,36 @@ class SelfAttention(PackedModule):
         self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Dropout(dropout))
 
     def _pack(self):
-        wq, wk, wv = w16(self.to_q.weight), w16(self.to_k.weight), w16(self.to_v.weight)
-        return {
-            "wqkv": torch.cat([wq, wk, wv], 0).contiguous(),
-            "wkv": torch.cat([wk, wv], 0).contiguous(),
-            "wo": w16(self.to_out[0].weight),
-            "bo": f32(self.to_out[0].bias),
-        }
+        return {"wo": w16(self.to_out[0].weight), "bo": f32(self.to_out[0].bias)}
+
+    def _wqkv(self):
+        return torch.cat([w16(self.to_q.weight), w16(self.to_k.weight), w16(self.to_v.weight)], 0).contiguous()
+
+    def fold_qkv(self, norm: nn.LayerNorm) -> "ops.LnFold":
+        w = torch.cat([self.to_q.weight.detach(), self.to_k.weight.detach(), self.to_v.weight.detach()], 0)
+        return ops.fold_layernorm(w, None, norm.weight, norm.bias, norm.eps)
 
     def project_kv(self, x16: torch.Tensor) -> torch.Tensor:
-        return ops.gemm(x16, self.pk()["wkv"])
+        wkv = self.lazy("wkv", lambda: torch.cat([w16(self.to_k.weight), w16(self.to_v.weight)], 0).contiguous())
+        return ops.gemm(x16, wkv)
 
-    def _fwd(self, x16, B, N, residual=None, gate=1.0, extra_kv=None, n_extra=0, extra_batch=0, out=None):
-        """x16: normalised tokens [B*N, C].  extra_kv: [Be*n_extra, 2C] additional keys/values
-        (the object tokens of the gated block)."""
+    def _fwd(self, x16, B, N, residual=None, gate=1.0, extra_kv=None, n_extra=0, extra_batch=0, out=None, ln=None,
+             want_stats=False):
+        """x16: normalised tokens [B*N, C] -- or, with ln=(RowStats, LnFold), the un-normalised stream.
+        extra_kv: [Be*n_extra, 2C] additional keys/values (the object tokens of the gated block)."""
         p = self.pk()
         C = self.heads * self.dim_head
-        qkv = ops.gemm(x16, p["wqkv"])
+        if ln is not None:
+            st, f = ln
+            qkv = ops.gemm(x16, f.w, f.bias, ln=(st, f.colsum, f.eps))
+        else:
+            qkv = ops.gemm(x16, self.lazy("wqkv", self._wqkv))
         kw = {}
         if extra_kv is not None:
             kw = dict(k1=extra_kv[:, :C], v1=extra_kv[:, C:2 * C], n1=n_extra, kv1_batch=extra_batch)
         a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], batch=B, heads=self.heads,
                           head_dim=self.dim_head, nq=N, n0=N, scale=self.scale, **kw)
-        return ops.gemm(a, p["wo"], p["bo"], residual=residual, gate=gate, out=out)
+        return ops.gemm(a, p["wo"], p["bo"], residual=residual, gate=gate, out=out, want_stats=want_stats)
 
     def forward(self, x, grounding_input=None, drop_box_mask=False):
         x16, B, N = to_tokens(x)
@@ -197,8 +224,9 @@ class GatedSelfAttentionDense(PackedModule):
     def _pack(self):
         return {
             "wl": w16(self.linear.weight), "bl": f32(self.linear.bias),
-            "g1": f32(self.norm1.weight), "b1": f32(self.norm1.bias),
-            "g2": f32(self.norm2.weight), "b2": f32(self.norm2.bias),
+            "g1": f32(self.norm1.weight), "b1": f32(self.norm1.bias),  # objects: standalone LayerNorm (hoisted)
+            "qkv": self.attn.fold_qkv(self.norm1),
+            "ff": self.ff.net[0].fold(self.norm2),
             "tanh_attn": math.tanh(float(self.alpha_attn.detach().float().cpu())),
             "tanh_dense": math.tanh(float(self.alpha_dense.detach().float().cpu())),
         }
@@ -210,21 +238,23 @@ class GatedSelfAttentionDense(PackedModule):
         o = ops.layernorm(o, p["g1"], p["b1"], self.norm1.eps)
         return self.attn.project_kv(o)
 
-    def _fwd(self, x16, B, N, obj_kv, n_obj, obj_batch):
-        """In-place on x16 (the residual stream).  Identity when scale == 0 (the alpha=0 steps)."""
+    def _fwd(self, x16, stats, B, N, obj_kv, n_obj, obj_batch):
+        """In-place on x16 (the residual stream; `stats` = its RowStats).  Returns (x16, stats).  Identity
+        when scale == 0 (the alpha=0 steps)."""
         if self.scale == 0:
-            return x16
+            return x16, stats
         p = self.pk()
-        n = ops.layernorm(x16, p["g1"], p["b1"], self.norm1.eps)
-        x16 = self.attn._fwd(n, B, N, residual=x16, gate=float(self.scale) * p["tanh_attn"],
-                             extra_kv=obj_kv, n_extra=n_obj, extra_batch=obj_batch, out=x16)
-        n = ops.layernorm(x16, p["g2"], p["b2"], self.norm2.eps)
-        return self.ff._fwd(n, residual=x16, gate=float(self.scale) * p["tanh_dense"], out=x16)
+        x16, stats = self.attn._fwd(x16, B, N, residual=x16, gate=float(self.scale) * p["tanh_attn"],
+                                    extra_kv=obj_kv, n_extra=n_obj, extra_batch=obj_batch, out=x16,
+                                    ln=(stats, p["qkv"]), want_stats=True)
+        return self.ff._fwd(x16, residual=x16, gate=float(self.scale) * p["tanh_dense"], out=x16,
+                            ln=(stats, p["ff"]), want_stats=True)
 
     def forward(self, x, objs, grounding_input=None, drop_box_mask=False):
         x16, B, N = to_tokens(x)
         o16, Bo, n_obj = to_tokens(objs)
-        y = self._fwd(x16.clone(), B, N, self.project_objs(o16), n_obj, Bo)
+        x16 = x16.clone()
+        y, _ = self._fwd(x16, ops.row_stats(x16), B, N, self.project_objs(o16), n_obj, Bo)
         return y.view(B, N, -1).to(x.dtype)
 
 
@@ -249,20 +279,18 @@ class BasicTransformerBlock(PackedModule):
 
     def _pack(self):
         return {
-            "g1": f32(self.norm1.weight), "b1": f32(self.norm1.bias),
-            "g2": f32(self.norm2.weight), "b2": f32(self.norm2.bias),
-            "g3": f32(self.norm3.weight), "b3": f32(self.norm3.bias),
+            "qkv1": self.attn1.fold_qkv(self.norm1),
+            "q2": self.attn2.fold_q(self.norm2),
+            "ff": self.ff.net[0].fold(self.norm3),
         }
 
-    def _fwd(self, x16, B, N, ctx_kv, M, obj_kv, n_obj, obj_batch):
+    def _fwd(self, x16, stats, B, N, ctx_kv, M, obj_kv, n_obj, obj_batch):
+        """x16: the residual stream (updated in place), stats: its RowStats (from the GEMM that wrote it)."""
         p = self.pk()
-        n = ops.layernorm(x16, p["g1"], p["b1"], self.norm1.eps)
-        x16 = self.attn1._fwd(n, B, N, residual=x16, out=x16)
-        x16 = self.fuser._fwd(x16, B, N, obj_kv, n_obj, obj_batch)
-        n = ops.layernorm(x16, p["g2"], p["b2"], self.norm2.eps)
-        x16 = self.attn2._fwd(n, ctx_kv, B, N, M, residual=x16, out=x16)
-        n = ops.layernorm(x16, p["g3"], p["b3"], self.norm3.eps)
-        return self.ff._fwd(n, residual=x16, out=x16)
+        x16, stats = self.attn1._fwd(x16, B, N, residual=x16, out=x16, ln=(stats, p["qkv1"]), want_stats=True)
+        x16, stats = self.fuser._fwd(x16, stats, B, N, obj_kv, n_obj, obj_batch)
+        x16, stats = self.attn2._fwd(x16, ctx_kv, B, N, M, residual=x16, out=x16, ln=(stats, p["q2"]), want_stats=True)
+        return self.ff._fwd(x16, residual=x16, out=x16, ln=(stats, p["ff"]))
 
     def forward(self, x, context, objs, grounding_input=None, drop_box_mask=False):
         return self._forward(x, context, objs, grounding_input, drop_box_mask=drop_box_mask)
@@ -272,7 +300,8 @@ class BasicTransformerBlock(PackedModule):
         c16, _, M = to_tokens(context)
         o16, Bo, n_obj = to_tokens(objs)
         obj_kv = self.fuser.project_objs(o16) if self.fuser.scale != 0 else None
-        y = self._fwd(x16.clone(), B, N, self.attn2.project_kv(c16), M, obj_kv, n_obj, Bo)
+        x16 = x16.clone()
+        y = self._fwd(x16, ops.row_stats(x16), B, N, self.attn2.project_kv(c16), M, obj_kv, n_obj, Bo)
         return y.view(B, N, -1).to(x.dtype)
 
 
@@ -309,9 +338,11 @@ class SpatialTransformer(PackedModule):
         """x16 fp16 [B*H*W, C].  ctx_kvs / obj_kvs: one entry per transformer block."""
         p = self.pk()
         n = ops.groupnorm(x16, p["gn_g"], p["gn_b"], batch=B, hw=H * W, groups=32, eps=self.norm.eps, silu=False)
-        t = ops.gemm(n, p["w_in"], p["b_in"])
+        t, stats = ops.gemm(n, p["w_in"], p["b_in"], want_stats=True)
         for i, blk in enumerate(self.transformer_blocks):
-            t = blk._fwd(t, B, H * W, ctx_kvs[i], M, obj_kvs[i] if obj_kvs is not None else None, n_obj, obj_batch)
+            if i > 0:  # (depth > 1: the previous block's FF out-projection did not keep statistics)
+                stats = ops.row_stats(t)
+            t = blk._fwd(t, stats, B, H * W, ctx_kvs[i], M, obj_kvs[i] if obj_kvs is not None else None, n_obj, obj_batch)
         return ops.gemm(t, p["w_out"], p["b_out"], residual=x16)
 
     def forward(self, x, context, objs, grounding_input=None, drop_box_mask=False):

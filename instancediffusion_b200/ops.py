@@ -103,14 +103,66 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
         raise _lib.IdiffError(f"{name} must be contiguous in its last dimension")
 
 
+class RowStats:
+    """Per-row partial (sum, sum of squares) of a token matrix, fp32 [slots, rows, 2]: what a producer GEMM's
+    epilogue (or row_stats) leaves for the folded LayerNorm of the next GEMM (idiff_gemm_args.ln_*)."""
+    __slots__ = ("t", "slots")
+
+    def __init__(self, t: torch.Tensor, slots: int):
+        self.t, self.slots = t, slots
+
+
+class LnFold:
+    """LayerNorm folded into the GEMM that consumes its output: w = fp16(W * gamma) (already in the layout
+    the GEMM wants), colsum[n] = sum_k w[n, k] (fp32), bias = W beta + b (fp32), eps."""
+    __slots__ = ("w", "bias", "colsum", "eps")
+
+    def __init__(self, w, bias, colsum, eps):
+        self.w, self.bias, self.colsum, self.eps = w, bias, colsum, float(eps)
+
+
+def fold_layernorm(weight: torch.Tensor, bias: Optional[torch.Tensor], ln_weight: torch.Tensor, ln_bias: torch.Tensor,
+                   eps: float, pack=None) -> LnFold:
+    """LN(x) W^T + b = rstd (x W'^T - mean colsum(W')) + (W beta + b), W' = W * gamma (fp32 masters in).
+    `pack(w16, b32) -> (w16, b32)` re-lays rows out (GEGLU interleave) before the column sums are taken."""
+    W = weight.detach().float()
+    g = ln_weight.detach().float()
+    beta = ln_bias.detach().float()
+    w16 = (W * g[None, :]).to(HALF).contiguous()
+    b = W @ beta
+    if bias is not None:
+        b = b + bias.detach().float()
+    b = b.contiguous()
+    if pack is not None:
+        w16, b = pack(w16, b)
+    return LnFold(w16, b, w16.float().sum(dim=1).contiguous(), eps)
+
+
+def row_stats(x: torch.Tensor) -> RowStats:
+    """One-slot row statistics of an fp16 [rows, C] matrix (entry of the folded LayerNorm when the stream was
+    not written by a GEMM of this library)."""
+    lib = _lib.load()
+    _req(x, HALF, "x")
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+        raise _lib.IdiffError("row_stats input must be contiguous")
+    st = torch.empty((1, x2.shape[0], 2), dtype=torch.float32, device=x.device)
+    check(_launch("row_stats", 0.0, 2.0 * x2.numel(), lambda: lib.idiff_row_stats(
+        x2.data_ptr(), st.data_ptr(), x2.shape[0], x2.shape[1], _stream())), "idiff_row_stats")
+    return RowStats(st, 1)
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
          out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          gate: float = 1.0, rowadd: Optional[torch.Tensor] = None, rows_per_batch: int = 0,
          geglu: bool = False, silu: bool = False, gelu: bool = False,
          conv: Optional[Tuple[int, int, int, int]] = None,
-         out_nchw: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out_nchw: Optional[torch.Tensor] = None,
+         ln: Optional[Tuple["RowStats", torch.Tensor, float]] = None, want_stats: bool = False):
     """out = epilogue(a @ w.T).  a: fp16 [M,K] (or NHWC [B,H,W,Cin] flattened with conv=(B,H,W,Cin));
-    w: fp16 [N,K].  See idiff_gemm in include/idiff_b200.h."""
+    w: fp16 [N,K].  See idiff_gemm in include/idiff_b200.h.
+    ln = (RowStats of a's rows, colsum, eps): a is the un-normalised stream and w / bias are LayerNorm-folded
+    (fold_layernorm).  want_stats: also return the RowStats of the output rows -> (out, stats)."""
     lib = _lib.load()
     _req(a, HALF, "a")
     _req(w, HALF, "w")
@@ -165,10 +217,27 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     args.flags = flags
     if conv is not None:
         args.conv_b, args.conv_h, args.conv_w, args.conv_cin = conv
+    if ln is not None:
+        st, colsum, eps = ln
+        _req(colsum, torch.float32, "ln colsum")
+        if st.t.shape[1] != M or colsum.numel() != N:
+            raise _lib.IdiffError(f"gemm: LayerNorm fold shape mismatch (stats rows {st.t.shape[1]} vs M {M}, "
+                                  f"colsum {colsum.numel()} vs N {N})")
+        args.ln_stats_in = st.t.data_ptr()
+        args.ln_colsum = colsum.data_ptr()
+        args.ln_slots_in = st.slots
+        args.ln_eps = float(eps)
+    stats = None
+    if want_stats:
+        slots = lib.idiff_gemm_ln_slots(C.byref(args))
+        if slots <= 0:
+            check(-1, "idiff_gemm_ln_slots")
+        stats = RowStats(torch.empty((slots, M, 2), dtype=torch.float32, device=a.device), slots)
+        args.ln_stats_out = stats.t.data_ptr()
     kind = "conv3x3" if conv is not None else ("gemm_geglu" if geglu else "gemm")
     nbytes = 2.0 * (M * K / (9 if conv is not None else 1) + N * K + M * n_out)
     check(_launch(kind, 2.0 * M * N * K, nbytes, lambda: lib.idiff_gemm(C.byref(args), _stream())), "idiff_gemm")
-    return result
+    return (result, stats) if want_stats else result
 
 
 def attention(q: torch.Tensor, k0: torch.Tensor, v0: torch.Tensor, *, batch: int, heads: int,

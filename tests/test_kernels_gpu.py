@@ -479,3 +479,66 @@ def test_segs_inconv_and_seg_tokens(cuda_device, S):
     ref0 = feat.float().reshape(B, -1, T).permute(0, 2, 1)[0] + pos
     _check(out[0], ref0, 1e-3, 1e-3, "seg_tokens has-seg sample")
     assert torch.equal(out[1], null_pos)
+
+
+# --------------------------------------------------------------------------------------------
+# LayerNorm folded across two GEMMs (idiff_gemm_args.ln_*): producer row statistics + consumer epilogue
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,C,mean_shift", [(4096, 320, 0.0), (1024, 640, 0.5), (300, 1280, -1.0), (64, 1280, 3.0)])
+def test_gemm_layernorm_fold(cuda_device, M, C, mean_shift):
+    """x = residual + gate * (a W0^T + b0) written by a producer GEMM with want_stats; then
+    LN(x) W1^T + b1 (plain) and GEGLU(LN(x) Wg^T + bg) through the folded consumers.  Reference: torch fp32
+    LayerNorm / linear on the fp16 x the producer stored.  Also: the statistics themselves, and the one-slot
+    row_stats entry point."""
+    ops = _ops()
+    a = _randn((M, C), cuda_device, 1.0, 1).half()
+    w0 = _randn((C, C), cuda_device, 1.0 / math.sqrt(C), 2).half()
+    b0 = _randn((C,), cuda_device, 0.5, 3) + mean_shift
+    res = _randn((M, C), cuda_device, 1.0, 4).half()
+    x, st = ops.gemm(a, w0, b0, residual=res, gate=0.7, want_stats=True)
+    xf = x.float()
+    # statistics: sum over slots == row sums of the stored x (up to fp16 rounding of x: the epilogue sums fp32)
+    got_sum = st.t[:, :, 0].sum(0)
+    got_sq = st.t[:, :, 1].sum(0)
+    _check(got_sum, xf.sum(1), 1e-3, 2e-2 * math.sqrt(C) / 16, f"ln stats sum M{M} C{C}")
+    _check(got_sq, (xf * xf).sum(1), 2e-3, 1e-2, f"ln stats sumsq M{M} C{C}")
+    st1 = ops.row_stats(x)
+    _check(st1.t[0, :, 0], xf.sum(1), 1e-5, 1e-3, "row_stats sum")
+    _check(st1.t[0, :, 1], (xf * xf).sum(1), 1e-5, 1e-3, "row_stats sumsq")
+
+    gamma = 1.0 + 0.3 * _randn((C,), cuda_device, 1.0, 5)
+    beta = 0.2 * _randn((C,), cuda_device, 1.0, 6)
+    eps = 1e-5
+    ln_ref = F.layer_norm(xf, (C,), gamma, beta, eps)
+    # plain consumer (QKV-like, N = 3C, no bias)
+    w1 = _randn((3 * C, C), cuda_device, 1.0 / math.sqrt(C), 7)
+    f1 = ops.fold_layernorm(w1, None, gamma, beta, eps)
+    ref1 = ln_ref @ w1.t()
+    for name, s in (("producer stats", st), ("row_stats", st1)):
+        out1 = ops.gemm(x, f1.w, f1.bias, ln=(s, f1.colsum, f1.eps))
+        _check(out1, ref1, 3e-3, 4e-3, f"ln-fold plain M{M} C{C} ({name})")
+    # GEGLU consumer (N = 8C, bias)
+    from instancediffusion_b200.packing import pack_geglu
+    wg = _randn((8 * C, C), cuda_device, 1.0 / math.sqrt(C), 8)
+    bg = _randn((8 * C,), cuda_device, 0.3, 9)
+    fg = ops.fold_layernorm(wg, bg, gamma, beta, eps, pack=pack_geglu)
+    outg = ops.gemm(x, fg.w, fg.bias, geglu=True, ln=(st, fg.colsum, fg.eps))
+    h = ln_ref @ wg.t() + bg
+    v, g = h.chunk(2, dim=-1)
+    _check(outg, v * F.gelu(g), 3e-3, 4e-3, f"ln-fold geglu M{M} C{C}")
+
+
+def test_gemm_stats_from_long_k_producer(cuda_device):
+    """FF out-projection at C=1280 (K = 5120 > 2560): the 8-warp direct epilogue also leaves row statistics."""
+    ops = _ops()
+    M, C, K = 2048, 1280, 5120
+    a = _randn((M, K), cuda_device, 1.0, 1).half()
+    w = _randn((C, K), cuda_device, 1.0 / math.sqrt(K), 2).half()
+    b = _randn((C,), cuda_device, 0.5, 3)
+    res = _randn((M, C), cuda_device, 1.0, 4).half()
+    x, st = ops.gemm(a, w, b, residual=res, want_stats=True)
+    xf = x.float()
+    _check(st.t[:, :, 0].sum(0), xf.sum(1), 1e-3, 0.1, "long-K stats sum")
+    _check(st.t[:, :, 1].sum(0), (xf * xf).sum(1), 2e-3, 1e-2, "long-K stats sumsq")
+    ref = res.float() + a.float() @ w.float().t() + b
+    _check(x, ref, 2e-3, 2e-3, "long-K producer output")

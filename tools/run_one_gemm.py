@@ -12,6 +12,16 @@ from instancediffusion_b200.packing import pack_geglu
 
 which = sys.argv[1]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+if "," in which:  # several shapes in one process, progress printed after each (hang localisation)
+    import subprocess
+    for w_ in which.split(","):
+        print("shape", w_, flush=True)
+        try:
+            rc = subprocess.run([sys.executable, __file__, w_, str(n)], timeout=60).returncode
+        except subprocess.TimeoutExpired:
+            rc = "TIMEOUT (hang)"
+        print("  rc", rc, flush=True)
+    sys.exit(0)
 dev = torch.device("cuda:0")
 B = 8
 r = lambda *s, sc=1.0: (torch.randn(*s, device=dev) * sc).half()
