@@ -159,6 +159,9 @@ int idiff_upsample_nearest2x(const void* x, void* y, int batch, int h, int w, in
 /* im2col for the stride-2 padding-1 3x3 Downsample conv (openaimodel.py:130-134):
    out [B*(H/2)*(W/2), 9*C], k = (ky*3+kx)*C + c */
 int idiff_im2col_s2(const void* x, void* y, int batch, int h, int w, int c, void* stream);
+/* same layout for the first-stage encoder's Downsample (diffusionmodules/model.py:70-74): F.pad (0,1,0,1)
+   then conv3x3 stride 2 padding 0, i.e. taps at (2*oy + ky, 2*ox + kx) with zero fill past the far edges */
+int idiff_im2col_s2_pad01(const void* x, void* y, int batch, int h, int w, int c, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * idiff_fourier_embed: UniFusion instance-token builder front end
@@ -218,6 +221,18 @@ int idiff_seg_tokens(const void* feat, const void* null_pos, const float* pos, c
 /* y = x * sigmoid(x) on fp16 (the nn.SiLU in front of ResBlock.emb_layers, openaimodel.py:200, when
    a ResBlock is driven through its module-level forward; the UNet path fuses it into a GEMM epilogue) */
 int idiff_silu_f16(const void* x, void* y, long n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * First-stage decoder (AutoencoderKL.decode, ldm/models/autoencoder.py:33-37; Decoder, model.py:462-569):
+ * convolutions / 1x1 projections are idiff_gemm calls, GroupNorm+swish idiff_groupnorm; these are the rest.
+ * ------------------------------------------------------------------------------------------- */
+/* autoencoder.py:34-35: y = post_quant_conv(z * inv_scale) (1x1, channels -> channels; w fp32 [C][C], bias [C])
+   from fp32 NCHW (B, C, HW) to fp16 NHWC [B*HW, 64] (channels >= C zero: the conv3x3 operand granularity) */
+int idiff_vae_latent_in(const float* z, const float* w, const float* bias, float inv_scale, void* out,
+                        int batch, int channels, int hw, void* stream);
+/* in-place softmax over the n columns of each of `rows` fp16 rows (row stride ld elements), fp32 arithmetic:
+   the attention weights of AttnBlock (model.py:185-187); the 1/sqrt(c) scale is folded into the q projection */
+int idiff_softmax_rows(void* x, int rows, int n, long ld, void* stream);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,7 @@ SIGNATURES = {
     "idiff_nhwc_f16_to_nchw_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "idiff_upsample_nearest2x": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "idiff_im2col_s2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "idiff_im2col_s2_pad01": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "idiff_fourier_embed": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "idiff_plms_update": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _f, _vp, _vp, _l, _vp]),
     "idiff_latent_mean": (_i, [_vp, _i, _vp, _l, _vp]),
@@ -77,6 +78,8 @@ SIGNATURES = {
     "idiff_patchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "idiff_dwconv7x7": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "idiff_seg_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "idiff_vae_latent_in": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp]),
+    "idiff_softmax_rows": (_i, [_vp, _i, _i, _l, _vp]),
 }
 
 _lib = None

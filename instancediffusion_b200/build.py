@@ -13,7 +13,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libidiff_b200.so")
-SOURCES = ["host.cu", "gemm2.cu", "attention.cu", "attention2.cu", "norm.cu", "scaleu.cu", "elementwise.cu", "convnext.cu"]
+SOURCES = ["host.cu", "gemm2.cu", "attention.cu", "attention2.cu", "norm.cu", "scaleu.cu", "elementwise.cu", "convnext.cu", "vae.cu"]
 HEADERS = ["common.cuh", "host.cuh", os.path.join("..", "..", "include", "idiff_b200.h")]
 
 NVCC_FLAGS = [

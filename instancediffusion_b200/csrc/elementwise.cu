@@ -61,8 +61,10 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 }
 
 // im2col for conv3x3 stride 2 pad 1 (openaimodel.py:130-134): out [B*Ho*Wo, 9*C]
+// pad_lo = 1: padding 1 on every side (openaimodel.py:130-134); pad_lo = 0: the first-stage encoder's
+// asymmetric F.pad (0,1,0,1) + stride-2 padding-0 convolution (diffusionmodules/model.py:70-74)
 __global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W,
-                                 int CV) {
+                                 int CV, int pad_lo) {
   pdl_launch_dependents();  // programmatic dependent launch: the next kernel may start its prologue
   pdl_wait();               // ... and this one touches global memory only after its predecessor finished
   const int Ho = H >> 1, Wo = W >> 1;
@@ -77,7 +79,7 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict_
     t /= Wo;
     const int oy = (int)(t % Ho);
     const int b = (int)(t / Ho);
-    const int iy = 2 * oy - 1 + tap / 3, ix = 2 * ox - 1 + tap % 3;
+    const int iy = 2 * oy - pad_lo + tap / 3, ix = 2 * ox - pad_lo + tap % 3;
     y[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? x[(((long)b * H + iy) * W + ix) * CV + cv] : zero;
   }
 }
@@ -237,7 +239,15 @@ extern "C" int idiff_upsample_nearest2x(const void* x, void* y, int batch, int h
 extern "C" int idiff_im2col_s2(const void* x, void* y, int batch, int h, int w, int c, void* stream) {
   IDIFF_REQUIRE(x && y && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "idiff_im2col_s2: bad arguments");
   const long total = (long)batch * (h / 2) * (w / 2) * 9 * (c / 8);
-  IDIFF_CHECK_CUDA(launch_pdl(im2col_s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),  reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), batch, h, w, c / 8));
+  IDIFF_CHECK_CUDA(launch_pdl(im2col_s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),  reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), batch, h, w, c / 8, 1));
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int idiff_im2col_s2_pad01(const void* x, void* y, int batch, int h, int w, int c, void* stream) {
+  IDIFF_REQUIRE(x && y && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "idiff_im2col_s2_pad01: bad arguments");
+  const long total = (long)batch * (h / 2) * (w / 2) * 9 * (c / 8);
+  IDIFF_CHECK_CUDA(launch_pdl(im2col_s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),  reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), batch, h, w, c / 8, 0));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

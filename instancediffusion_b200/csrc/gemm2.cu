@@ -86,9 +86,13 @@ struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int BOX_BYTES = 32 * CHUNK * 2;                       // 1 KiB
-  static constexpr int STG_BYTES = TMA_EPI ? 4 * NCHT * BOX_BYTES : 0;  // [quarter][chunk] boxes
+  // TMA epilogue staging: one [32 rows x BN/2 columns] fp16 box per epilogue warp (row-major, no swizzle):
+  // the residual lands in it with ONE bulk-tensor load per warp and tile, the result leaves with ONE store
+  static constexpr int WBOX_BYTES = 32 * (BN / 2) * 2;
+  static constexpr int STG_BYTES = TMA_EPI ? EW * WBOX_BYTES : 0;
   static constexpr int TAB_BYTES = 2 * EPI_TAB_PB * BN * 4;
-  static constexpr int BAR_BYTES = 512;  // 2*STAGES + 4 + MAX_EPI_WARPS mbarriers (<= 32 x 8 B) + the TMEM base slot
+  static constexpr int BAR_BYTES = 1024;  // 2*STAGES + 4 + MAX_EPI_WARPS mbarriers (<= 32 x 8 B) + the TMEM base slot;
+                                          // 1 KiB keeps the staging boxes 1024-byte aligned (SWIZZLE_128B boxes)
   static constexpr int FIXED = 1024 + BAR_BYTES + TAB_BYTES + STG_BYTES;
   static constexpr int STAGES_FIT = (227 * 1024 - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
@@ -162,6 +166,162 @@ IDIFF_DEVICE int ld_acquire_gpu(const int* p) {
 }
 IDIFF_DEVICE void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- packed fp32x2 arithmetic (FADD2 / FFMA2: two values per issue slot) for the epilogue ----
+IDIFF_DEVICE uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+IDIFF_DEVICE void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+IDIFF_DEVICE uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+IDIFF_DEVICE uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+IDIFF_DEVICE void lds_f2x2(uint32_t a, uint64_t& p0, uint64_t& p1) {  // four floats as two packed pairs
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];\n" : "=l"(p0), "=l"(p1) : "r"(a));
+}
+
+// The short-K epilogue of one warp, specialised at compile time (the all-flags loop spent ~60 of its 142
+// instructions per 16-column chunk on uniform flag tests and trace hooks, and the warp is instruction-latency
+// bound: two epilogue warps per scheduler, ~6.5 clk per dependent instruction; ncu source view, profiles/).
+// Plain linear layer: acc (+ LayerNorm fold) + bias, optional gate * x + residual, optional row statistics.
+// Packed fp32x2 arithmetic throughout.  trow: TMEM address of this warp's lane quarter; tab_s: epilogue table
+// (row 0 bias, row 1 column sums); row_s: this thread's row of the staging box; c_first: first accumulator
+// column of the warp; nlive: live 16-column chunks.
+template <int BN, int WCOLS, bool RES, bool LNI, bool LNO>
+IDIFF_DEVICE void epi_chunks_plain(uint32_t trow, uint32_t tab_s, uint32_t row_s, int c_first, int nlive, uint32_t lane,
+                                   float gate, float ln_rstd, float ln_b, float& ln_ps, float& ln_pq) {
+  const uint64_t gate2 = f2_pack(gate, gate), rstd2 = f2_pack(ln_rstd, ln_rstd), lnb2 = f2_pack(ln_b, ln_b);
+  uint64_t ps2 = 0ull, pq2 = 0ull;  // (+0.0f, +0.0f)
+#pragma unroll 1
+  for (int ch = 0; ch < nlive; ++ch) {
+    const int c0 = c_first + ch * CHUNK;
+    uint32_t v[CHUNK];
+    tmem_ld_32x32b_x16(trow + c0, v);
+    tmem_ld_wait();
+    uint64_t x2[CHUNK / 2];
+#pragma unroll
+    for (int j = 0; j < CHUNK / 2; ++j) x2[j] = f2_pack(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint64_t b0, b1;
+      lds_f2x2(tab_s + (c0 + 4 * q) * 4, b0, b1);
+      if (LNI) {  // y = rstd * acc + (-mean * rstd) * colsum + bias
+        uint64_t s0, s1;
+        lds_f2x2(tab_s + (BN + c0 + 4 * q) * 4, s0, s1);
+        x2[2 * q] = f2_fma(rstd2, x2[2 * q], f2_fma(lnb2, s0, b0));
+        x2[2 * q + 1] = f2_fma(rstd2, x2[2 * q + 1], f2_fma(lnb2, s1, b1));
+      } else {
+        x2[2 * q] = f2_add(x2[2 * q], b0);
+        x2[2 * q + 1] = f2_add(x2[2 * q + 1], b1);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t slot = (WCOLS == 64) ? row_s + ((static_cast<uint32_t>(ch * 2 + q) ^ (lane & 7u)) << 4)
+                                          : row_s + ch * (CHUNK * 2) + (q << 4);
+      uint64_t y2[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y2[j] = x2[4 * q + j];
+      if (RES) {
+        uint32_t ru[4];
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+                     : "=r"(ru[0]), "=r"(ru[1]), "=r"(ru[2]), "=r"(ru[3]) : "r"(slot));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_half2(ru[j]);
+          y2[j] = f2_fma(gate2, y2[j], f2_pack(f.x, f.y));
+        }
+      }
+      if (LNO) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ps2 = f2_add(ps2, y2[j]);
+          pq2 = f2_fma(y2[j], y2[j], pq2);
+        }
+      }
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float lo, hi;
+        f2_unpack(y2[j], lo, hi);
+        o[j] = pack_half2(lo, hi);
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(slot), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                   : "memory");
+    }
+  }
+  if (LNO) {
+    float a, b;
+    f2_unpack(ps2, a, b);
+    ln_ps += a + b;
+    f2_unpack(pq2, a, b);
+    ln_pq += a + b;
+  }
+}
+
+// GEGLU projection: (value (+LN) + b) * gelu(gate (+LN) + b); value chunk c0, its gates BN/2 columns further on
+template <int BN, bool LNI>
+IDIFF_DEVICE void epi_chunks_geglu(uint32_t trow, uint32_t tab_s, uint32_t row_s, int c_first, int nlive, uint32_t lane,
+                                   float ln_rstd, float ln_b) {
+  const uint64_t rstd2 = f2_pack(ln_rstd, ln_rstd), lnb2 = f2_pack(ln_b, ln_b);
+#pragma unroll 1
+  for (int ch = 0; ch < nlive; ++ch) {
+    const int c0 = c_first + ch * CHUNK;
+    uint32_t v[CHUNK], g[CHUNK];
+    tmem_ld_32x32b_x16(trow + c0, v);
+    tmem_ld_32x32b_x16(trow + BN / 2 + c0, g);
+    tmem_ld_wait();
+    float x[CHUNK];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint64_t xv[2], gv[2], bv0, bv1, bg0, bg1;
+      xv[0] = f2_pack(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]));
+      xv[1] = f2_pack(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+      gv[0] = f2_pack(__uint_as_float(g[4 * q]), __uint_as_float(g[4 * q + 1]));
+      gv[1] = f2_pack(__uint_as_float(g[4 * q + 2]), __uint_as_float(g[4 * q + 3]));
+      lds_f2x2(tab_s + (c0 + 4 * q) * 4, bv0, bv1);
+      lds_f2x2(tab_s + (BN / 2 + c0 + 4 * q) * 4, bg0, bg1);
+      if (LNI) {
+        uint64_t sv0, sv1, sg0, sg1;
+        lds_f2x2(tab_s + (BN + c0 + 4 * q) * 4, sv0, sv1);
+        lds_f2x2(tab_s + (BN + BN / 2 + c0 + 4 * q) * 4, sg0, sg1);
+        xv[0] = f2_fma(rstd2, xv[0], f2_fma(lnb2, sv0, bv0));
+        xv[1] = f2_fma(rstd2, xv[1], f2_fma(lnb2, sv1, bv1));
+        gv[0] = f2_fma(rstd2, gv[0], f2_fma(lnb2, sg0, bg0));
+        gv[1] = f2_fma(rstd2, gv[1], f2_fma(lnb2, sg1, bg1));
+      } else {
+        xv[0] = f2_add(xv[0], bv0);
+        xv[1] = f2_add(xv[1], bv1);
+        gv[0] = f2_add(gv[0], bg0);
+        gv[1] = f2_add(gv[1], bg1);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float a0, a1, g0, g1;
+        f2_unpack(xv[h], a0, a1);
+        f2_unpack(gv[h], g0, g1);
+        x[4 * q + 2 * h] = a0 * gelu_erf_f(g0);
+        x[4 * q + 2 * h + 1] = a1 * gelu_erf_f(g1);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {  // GEGLU boxes are 64 columns wide: SWIZZLE_128B
+      const uint32_t slot = row_s + ((static_cast<uint32_t>(ch * 2 + q) ^ (lane & 7u)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(slot), "r"(pack_half2(x[8 * q], x[8 * q + 1])),
+                   "r"(pack_half2(x[8 * q + 2], x[8 * q + 3])), "r"(pack_half2(x[8 * q + 4], x[8 * q + 5])),
+                   "r"(pack_half2(x[8 * q + 6], x[8 * q + 7]))
+                   : "memory");
+    }
+  }
 }
 
 constexpr int MODE_PLAIN = 0;  // bias / row-add table, optional SiLU, optional gate*x + residual, fp16 out
@@ -393,7 +553,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint4 resv[TMA_EPI ? 1 : NCH][2];
       const bool has_res = owner && (TMA_EPI || row_ok) && p.residual != nullptr && !geglu;
       // staging boxes of this warp: box ch holds rows [32*quarter, +32) x 16 output columns
-      uint8_t* wstage = s_stage + (TMA_EPI ? (quarter * C::NCHT + cb) * C::BOX_BYTES : 0);
+      uint8_t* wstage = s_stage + (TMA_EPI ? ew * C::WBOX_BYTES : 0);
+      constexpr int WCOLS = geglu ? BN / 4 : BN / 2;        // output columns of this warp (one staging-box row)
+      const int wcol0 = out_col_base + cb * CHUNK;          // ... starting here
+      const bool wbox_live = wcol0 < n_out_total;           // (a ragged last N tile may leave a warp without columns)
       // tile-local coordinates of this warp's first row, for the output / residual tensor maps
       int tc1 = 0, tc2 = 0, tc3 = 0;
       if (TMA_EPI && owner) {
@@ -410,20 +573,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // the previous tile's stores must have finished reading the boxes before they are refilled
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
-        if (has_res && lane == 0) {
-          int nbox = 0;
-#pragma unroll
-          for (int ch = 0; ch < NCH; ++ch)
-            if (ch < nv && out_col_base + chunk_col(ch) < n_out_total) ++nbox;
-          mbar_expect_tx(&res_bar[ew], nbox * C::BOX_BYTES);
-#pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) {
-            const int col = out_col_base + chunk_col(ch);
-            if (ch < nv && col < n_out_total) {
-              if (p.conv) tma_load_4d(wstage + ch * C::BOX_BYTES, &tmR, &res_bar[ew], col, tc1, tc2, tc3);
-              else tma_load_2d(wstage + ch * C::BOX_BYTES, &tmR, &res_bar[ew], col, tc1);
-            }
-          }
+        if (has_res && wbox_live && lane == 0) {
+          // one box per warp; rows / columns outside the tensor arrive as zeros and still count as bytes
+          mbar_expect_tx(&res_bar[ew], 32 * WCOLS * 2);
+          if (p.conv) tma_load_4d(wstage, &tmR, &res_bar[ew], wcol0, tc1, tc2, tc3);
+          else tma_load_2d(wstage, &tmR, &res_bar[ew], wcol0, tc1);
         }
       }
       if (!TMA_EPI && has_res) {
@@ -475,7 +629,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const float inv_k = 1.0f / (float)p.K;
         const float mean = a * inv_k;
         ln_rstd = rsqrtf(fmaxf(q * inv_k - mean * mean, 0.f) + p.ln_eps);
-        ln_nmean = -mean;
+        ln_nmean = -mean * ln_rstd;  // y = rstd * acc + (-mean * rstd) * colsum + bias: two FMAs per element
       }
       float ln_ps = 0.f, ln_pq = 0.f;  // producer side: partial (sum, sumsq) of this warp's output columns
       mbar_wait(&tmem_full[acc], (sc >> 1) & 1);
@@ -574,7 +728,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // outside the per-element loops (the first version spent ~40 instructions per element on
         // address arithmetic and predicates and was issue-bound; see profiles/).
         if (sc == 0 && threadIdx.x == 128) stamp(4);
-        if (TMA_EPI && has_res) {
+        if (TMA_EPI && has_res && wbox_live) {
           mbar_wait(&res_bar[ew], res_phase);
           res_phase ^= 1;
         }
@@ -587,17 +741,37 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           // (26 % stall_no_inst, generic LD for shared operands; profiles/).
           const int cbase = cb * CHUNK;
           const uint32_t tab_s = smem_u32(tab_row);
-          const uint32_t box_s = smem_u32(wstage) + lane * 32;
-          const uint32_t sw16 = ((lane >> 2) & 1) << 4;
+          const uint32_t row_s = smem_u32(wstage) + lane * (WCOLS * 2);  // this thread's row of the staging box
           auto lds4 = [](uint32_t a, float (&f)[4]) {
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
                          : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(a));
           };
+          // live chunks of this warp (a ragged last N tile ends early; warp-uniform)
+          int nlive = 0;
+          if (wbox_live) {
+            nlive = (n_out_total - wcol0 + CHUNK - 1) / CHUNK;
+            nlive = nlive < nv ? nlive : nv;
+          }
+          const bool lni = p.ln_in != nullptr, lno = p.ln_out != nullptr;
+          bool fast = false;
+          if constexpr (geglu) {
+            fast = true;
+            if (lni) epi_chunks_geglu<BN, true>(trow, tab_s, row_s, cbase, nlive, lane, ln_rstd, ln_nmean);
+            else epi_chunks_geglu<BN, false>(trow, tab_s, row_s, cbase, nlive, lane, ln_rstd, ln_nmean);
+          } else if (!slow_rowadd && !do_silu && !do_gelu) {
+            fast = true;
+            // (row statistics are only ever asked of residual-free proj_in GEMMs or of residual GEMMs; a fold
+            // consumer never has a residual: five live combinations)
+#define IDIFF_EPI(R, I, O) epi_chunks_plain<BN, WCOLS, R, I, O>(trow, tab_s, row_s, cbase, nlive, lane, gate, ln_rstd, ln_nmean, ln_ps, ln_pq)
+            if (has_res) { if (lno) IDIFF_EPI(true, false, true); else IDIFF_EPI(true, false, false); }
+            else if (lni) { if (lno) IDIFF_EPI(false, true, true); else IDIFF_EPI(false, true, false); }
+            else { if (lno) IDIFF_EPI(false, false, true); else IDIFF_EPI(false, false, false); }
+#undef IDIFF_EPI
+          }
 #pragma unroll 1
-          for (int ch = 0; ch < nv; ++ch) {
+          for (int ch = 0; ch < (fast ? 0 : nlive); ++ch) {  // all-flags fallback (SiLU / GELU / per-row add layers)
             const int c0 = cbase + ch * CHUNK;
             const int out_c = out_col_base + c0;
-            if (out_c >= n_out_total) break;  // warp-uniform
             uint32_t v[CHUNK];
             float x[CHUNK];
             tmem_ld_32x32b_x16(trow + c0, v);
@@ -614,23 +788,27 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               if (p.ln_in != nullptr) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  float sv[4], sg[4];
+                  float sv[4], sg[4], bv[4], bg[4];
                   lds4(tab_s + (BN + c0 + 4 * q) * 4, sv);
                   lds4(tab_s + (BN + BN / 2 + c0 + 4 * q) * 4, sg);
+                  lds4(tab_s + (c0 + 4 * q) * 4, bv);
+                  lds4(tab_s + (BN / 2 + c0 + 4 * q) * 4, bg);
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
-                    x[4 * q + j] = ln_rstd * fmaf(ln_nmean, sv[j], x[4 * q + j]);
-                    gx[4 * q + j] = ln_rstd * fmaf(ln_nmean, sg[j], gx[4 * q + j]);
+                    const float xv = fmaf(ln_rstd, x[4 * q + j], fmaf(ln_nmean, sv[j], bv[j]));
+                    const float gv = fmaf(ln_rstd, gx[4 * q + j], fmaf(ln_nmean, sg[j], bg[j]));
+                    x[4 * q + j] = xv * gelu_erf_f(gv);
                   }
                 }
-              }
+              } else {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float bv[4], bg[4];
-                lds4(tab_s + (c0 + 4 * q) * 4, bv);
-                lds4(tab_s + (BN / 2 + c0 + 4 * q) * 4, bg);
+                for (int q = 0; q < 4; ++q) {
+                  float bv[4], bg[4];
+                  lds4(tab_s + (c0 + 4 * q) * 4, bv);
+                  lds4(tab_s + (BN / 2 + c0 + 4 * q) * 4, bg);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) x[4 * q + j] = (x[4 * q + j] + bv[j]) * gelu_erf_f(gx[4 * q + j] + bg[j]);
+                  for (int j = 0; j < 4; ++j) x[4 * q + j] = (x[4 * q + j] + bv[j]) * gelu_erf_f(gx[4 * q + j] + bg[j]);
+                }
               }
             } else {
               tmem_ld_wait();
@@ -639,18 +817,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               if (p.ln_in != nullptr) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  float sv[4];
+                  float sv[4], bv[4];
                   lds4(tab_s + (BN + c0 + 4 * q) * 4, sv);
+                  lds4(tab_s + (c0 + 4 * q) * 4, bv);
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) x[4 * q + j] = ln_rstd * fmaf(ln_nmean, sv[j], x[4 * q + j]);
+                  for (int j = 0; j < 4; ++j) x[4 * q + j] = fmaf(ln_rstd, x[4 * q + j], fmaf(ln_nmean, sv[j], bv[j]));
                 }
-              }
+              } else {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float bv[4];
-                lds4(tab_s + (c0 + 4 * q) * 4, bv);
+                for (int q = 0; q < 4; ++q) {
+                  float bv[4];
+                  lds4(tab_s + (c0 + 4 * q) * 4, bv);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) x[4 * q + j] += bv[j];
+                  for (int j = 0; j < 4; ++j) x[4 * q + j] += bv[j];
+                }
               }
               if (slow_rowadd && row_ok) {
 #pragma unroll
@@ -665,12 +845,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 for (int j = 0; j < CHUNK; ++j) x[j] = gelu_erf_f(x[j]);
               }
             }
-            // box `ch`: row `lane` is 32 B; SWIZZLE_32B puts 16-byte chunk q at (q ^ ((lane >> 2) & 1)).
-            // The residual (if any) was landed here by TMA; the result replaces it in place.
-            const uint32_t boxa = box_s + ch * C::BOX_BYTES;
+            // The residual (if any) was landed in the box by TMA; the result replaces it in place.  (Rows are
+            // WCOLS * 2 bytes apart: 16-byte accesses of eight consecutive lanes collide two ways at most.)
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-              const uint32_t slot = boxa + ((q << 4) ^ sw16);
+              // 64-column boxes (128-byte rows) are SWIZZLE_128B: 16-byte chunk i of row r sits at i ^ (r & 7);
+              // wider rows are unswizzled (160 / 192-byte pitch: two / four-way conflicts at most)
+              const uint32_t slot = (WCOLS == 64) ? row_s + ((static_cast<uint32_t>(ch * 2 + q) ^ (lane & 7u)) << 4)
+                                                  : row_s + ch * (CHUNK * 2) + (q << 4);
               float y[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) y[j] = x[8 * q + j];
@@ -696,13 +878,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                            "r"(pack_half2(y[2], y[3])), "r"(pack_half2(y[4], y[5])), "r"(pack_half2(y[6], y[7]))
                            : "memory");
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              if (p.conv) tma_store_4d(&tmO, wstage + ch * C::BOX_BYTES, out_c, tc1, tc2, tc3);
-              else tma_store_2d(&tmO, wstage + ch * C::BOX_BYTES, out_c, tc1);
-            }
           }
+          // one proxy fence and ONE bulk-tensor store per warp and tile (per 16-column chunk they were a
+          // ~700-clock serial tail of every trip: tools/trace_gemm.py); columns / rows outside the tensor
+          // are clipped by the store
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && wbox_live) {
+            if (p.conv) tma_store_4d(&tmO, wstage, wcol0, tc1, tc2, tc3);
+            else tma_store_2d(&tmO, wstage, wcol0, tc1);
+          }
+          if (sc == 0 && threadIdx.x == 128) stamp(11);
         } else {
         // Chunks are processed in groups of up to GROUP: all accumulator loads of a group are issued
         // before one wait, all results are staged before one proxy fence / warp sync, and the
@@ -1020,22 +1206,24 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream, bool want_sk) {
     p.U_sk = 0;
   }
 
-  // output / residual views for the TMA epilogue: [32 rows x 16 cols] boxes, SWIZZLE_32B
+  // output / residual views for the TMA epilogue: one [32 rows x BN/2 (GEGLU: BN/4) columns] box per warp,
+  // row-major in shared memory (no swizzle)
   CUtensorMap tmO = tmA, tmR = tmA;
   if (TMA_EPI) {
     const int n_out = (MODE == MODE_GEGLU) ? a->N / 2 : a->N;
+    const uint32_t wcols = (MODE == MODE_GEGLU) ? BN / 4 : BN / 2;
     auto make = [&](CUtensorMap* m, const void* base, int ld) -> int {
       if (p.conv) {
         const int pws = p.PW < 32 ? p.PW : 32;
         const uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Bn};
         const uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)p.W * ld * 2, (uint64_t)p.H * p.W * ld * 2};
-        const uint32_t box[4] = {(uint32_t)CHUNK, (uint32_t)pws, (uint32_t)(32 / pws), 1u};
-        return encode_tmap_f16_sw(m, base, 4, dims, strides, box, 32);
+        const uint32_t box[4] = {wcols, (uint32_t)pws, (uint32_t)(32 / pws), 1u};
+        return encode_tmap_f16_sw(m, base, 4, dims, strides, box, wcols == 64 ? 128 : 0);
       }
       const uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)a->M};
       const uint64_t strides[1] = {(uint64_t)ld * 2};
-      const uint32_t box[2] = {(uint32_t)CHUNK, 32u};
-      return encode_tmap_f16_sw(m, base, 2, dims, strides, box, 32);
+      const uint32_t box[2] = {wcols, 32u};
+      return encode_tmap_f16_sw(m, base, 2, dims, strides, box, wcols == 64 ? 128 : 0);
     };
     if (make(&tmO, a->out, a->ldo)) return -1;
     if (a->residual && make(&tmR, a->residual, a->ldr)) return -1;
@@ -1135,16 +1323,10 @@ struct Resolved {
   bool tma_epi, sk;
 };
 static Resolved resolve(const idiff_gemm_args* a) {
-  // epilogue warps of the short-K layers: IDIFF_GEMM_EW = 8 (default until the wider ones are verified) / 12 / 16
-  static const int ew_short = []() {
-    const char* e = getenv("IDIFF_GEMM_EW");
-    const int v = e ? atoi(e) : 8;
-    return (v == 12 || v == 13 || v == 16 || v == 17) ? v : 8;  // 13 / 17: 12 / 16 warps without setmaxnreg (diagnostic)
-  }();
   Resolved r;
   // GEGLU: one 256-column accumulator tile = 128 value columns + their 128 gates (packing.py)
   if (a->flags & IDIFF_EPI_GEGLU) {
-    r = {256, MODE_GEGLU, ew_short, true, plan_gemm(a, 256).sk};
+    r = {256, MODE_GEGLU, 8, true, plan_gemm(a, 256).sk};
     return r;
   }
   if (a->flags & IDIFF_OUT_F32_NCHW) {
@@ -1155,30 +1337,24 @@ static Resolved resolve(const idiff_gemm_args* a) {
   // long K (3x3 convolutions): deep operand ring, direct epilogue hidden behind the next mainloop
   const bool tma_epi = ((a->K + BK - 1) / BK) <= kTmaEpiMaxKB;
   const Plan pl = plan_gemm(a, false);
-  r = {pl.bn, MODE_PLAIN, tma_epi ? ew_short : 8, tma_epi, pl.sk};
+  r = {pl.bn, MODE_PLAIN, 8, tma_epi, pl.sk};
   return r;
 }
 
 template <int BN>
 static int launch_plain(const Resolved& r, const idiff_gemm_args* a, cudaStream_t stream) {
   if (!r.tma_epi) return launch<BN, MODE_PLAIN, false, 8>(a, stream, r.sk);
-  if (r.ew == 16) return launch<BN, MODE_PLAIN, true, 16>(a, stream, r.sk);
-  if (r.ew == 12) return launch<BN, MODE_PLAIN, true, 12>(a, stream, r.sk);
-  if (r.ew == 13) return launch<BN, MODE_PLAIN, true, 12, false>(a, stream, r.sk);
-  if (r.ew == 17) return launch<BN, MODE_PLAIN, true, 16, false>(a, stream, r.sk);
   return launch<BN, MODE_PLAIN, true, 8>(a, stream, r.sk);
 }
 
-// One instantiation per (tile width, epilogue mode, epilogue warps): each kernel carries only its own
-// mode's code (an all-modes kernel was ~140 KB of SASS and stalled on instruction fetch: 26 %
-// stall_no_inst, profiles/).
+// One instantiation per (tile width, epilogue mode): each kernel carries only its own mode's code (an
+// all-modes kernel was ~140 KB of SASS and stalled on instruction fetch: 26 % stall_no_inst, profiles/).
+// The epilogue-warp count is a template parameter of the kernel; 12 and 16 warps (three / four column parts,
+// 152 / 104 registers) were measured SLOWER than 8 at every UNet shape (profiles/README.md, round 2: qkv C320
+// 41 -> 45 -> 66 us) and are not instantiated.
 int gemm_v2(const idiff_gemm_args* a, cudaStream_t stream) {
   const Resolved r = resolve(a);
-  if (r.mode == MODE_GEGLU) {
-    return (r.ew == 16 || r.ew == 17) ? launch<256, MODE_GEGLU, true, 16>(a, stream, r.sk)
-           : (r.ew == 12 || r.ew == 13) ? launch<256, MODE_GEGLU, true, 12>(a, stream, r.sk)
-                                        : launch<256, MODE_GEGLU, true, 8>(a, stream, r.sk);
-  }
+  if (r.mode == MODE_GEGLU) return launch<256, MODE_GEGLU, true, 8>(a, stream, r.sk);
   if (r.mode == MODE_NCHW) return launch<128, MODE_NCHW, false, 8>(a, stream, r.sk);
   switch (r.bn) {
     case 256: return launch_plain<256>(r, a, stream);
@@ -1191,7 +1367,7 @@ int gemm_v2(const idiff_gemm_args* a, cudaStream_t stream) {
 // slots of the LayerNorm partial statistics a producer GEMM with these arguments writes per row
 int ln_slots_of(const idiff_gemm_args* a) {
   const Resolved r = resolve(a);
-  return ((a->N + r.bn - 1) / r.bn) * ((r.ew == 13 ? 12 : r.ew == 17 ? 16 : r.ew) / 4);
+  return ((a->N + r.bn - 1) / r.bn) * (r.ew / 4);
 }
 
 }  // namespace v2

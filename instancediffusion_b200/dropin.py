@@ -9,11 +9,12 @@ SURVEY.md section 8b resolve to this package's mirrors:
     ldm.models.diffusion.{plms, plms_instance, ldm, ddpm}
     grounding_input.text_grounding_tokinzer_input
     utils.model  (set_alpha_scale / alpha_generator only; everything else stays the reference's)
+    ldm.models.autoencoder, ldm.modules.diffusionmodules.model   (first stage: AutoencoderKL.decode right
+        after the sampler loop, inference.py:96; `install(first_stage=False)` leaves it to the reference)
 
 With a reference checkout on sys.path (or passed as `reference_root` / $IDIFF_REF) the *parent*
 packages stay the reference's own (`ldm`, `ldm.modules`, `ldm.models`, `utils` are namespace
-packages there), so every module that is not mirrored -- `ldm.models.autoencoder`,
-`ldm.modules.diffusionmodules.model`, `ldm.modules.encoders.modules`, `utils.input`,
+packages there), so every module that is not mirrored -- `ldm.modules.encoders.modules`, `utils.input`,
 `utils.checkpoint`, `dataset.*` -- keeps importing from the reference's files, and a name a
 mirrored module does not define (e.g. `ldm.modules.attention.LinearAttention`, imported by the
 reference's VAE, diffusionmodules/model.py:9) is fetched lazily from the reference's own file of
@@ -41,6 +42,10 @@ _MAP = {
     "ldm.models.diffusion.ldm": "instancediffusion_b200.ldm.models.diffusion.ldm",
     "ldm.models.diffusion.ddpm": "instancediffusion_b200.ldm.models.diffusion.ddpm",
     "grounding_input.text_grounding_tokinzer_input": "instancediffusion_b200.grounding_input.text_grounding_tokinzer_input",
+}
+_FIRST_STAGE = {
+    "ldm.models.autoencoder": "instancediffusion_b200.ldm.models.autoencoder",
+    "ldm.modules.diffusionmodules.model": "instancediffusion_b200.ldm.modules.diffusionmodules.model",
 }
 _PKGS = {
     "ldm": "instancediffusion_b200.ldm",
@@ -108,11 +113,13 @@ def _bind(alias: str, module: types.ModuleType) -> None:
             setattr(sys.modules[parent], leaf, module)
 
 
-def install(shadow_utils_model: bool = True, reference_root: Optional[str] = None) -> Optional[str]:
+def install(shadow_utils_model: bool = True, reference_root: Optional[str] = None,
+            first_stage: bool = True) -> Optional[str]:
     """Alias the mirror leaf modules under the reference's import paths; returns the reference root
     that keeps serving the non-mirrored modules (None if no checkout is visible)."""
     root = find_reference_root(reference_root)
     from .utils import model as um
+    leaf_map = {**_MAP, **(_FIRST_STAGE if first_stage else {})}
     if root is not None:
         if root not in sys.path:
             sys.path.insert(0, root)
@@ -123,7 +130,7 @@ def install(shadow_utils_model: bool = True, reference_root: Optional[str] = Non
                 if getattr(m, "__name__", "").startswith("instancediffusion_b200"):
                     del sys.modules[stale]  # left over from a checkout-less install()
             importlib.import_module(pkg)
-        for alias, real in _MAP.items():
+        for alias, real in leaf_map.items():
             mirror = importlib.import_module(real)
             if os.path.isfile(os.path.join(root, *alias.split(".")) + ".py"):
                 _add_fallback(mirror, alias, root)
@@ -152,7 +159,7 @@ def install(shadow_utils_model: bool = True, reference_root: Optional[str] = Non
                 _bind("utils.model", shim)
         return root
     # no checkout: the mirrors' packages stand in as parents
-    for alias, real in {**_PKGS, **_MAP}.items():
+    for alias, real in {**_PKGS, **leaf_map}.items():
         sys.modules[alias] = importlib.import_module(real)
         _installed.append(alias)
     if shadow_utils_model:

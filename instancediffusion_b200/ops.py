@@ -354,13 +354,17 @@ def upsample_nearest2x(x: torch.Tensor, batch: int, h: int, w: int, out: Optiona
     return out
 
 
-def im2col_s2(x: torch.Tensor, batch: int, h: int, w: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def im2col_s2(x: torch.Tensor, batch: int, h: int, w: int, out: Optional[torch.Tensor] = None,
+              pad01: bool = False) -> torch.Tensor:
+    """Operand rows of a stride-2 3x3 convolution: padding 1 (UNet Downsample) or, pad01, the first-stage
+    encoder's F.pad (0,1,0,1) + padding 0."""
     lib = _lib.load()
     _req(x, HALF, "x")
     Cc = x.shape[-1]
     if out is None:
         out = torch.empty((batch * (h // 2) * (w // 2), 9 * Cc), dtype=HALF, device=x.device)
-    check(lib.idiff_im2col_s2(x.data_ptr(), out.data_ptr(), batch, h, w, Cc, _stream()), "idiff_im2col_s2")
+    fn = lib.idiff_im2col_s2_pad01 if pad01 else lib.idiff_im2col_s2
+    check(fn(x.data_ptr(), out.data_ptr(), batch, h, w, Cc, _stream()), "idiff_im2col_s2")
     return out
 
 
@@ -479,3 +483,30 @@ def seg_tokens(feat: torch.Tensor, null_pos: torch.Tensor, pos: torch.Tensor, se
     check(lib.idiff_seg_tokens(feat.data_ptr(), null_pos.data_ptr(), pos.data_ptr(), seg_sum.data_ptr(),
                                out.data_ptr(), batch, pixels, c, tokens, _stream()), "idiff_seg_tokens")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# first-stage decoder pieces (csrc/vae.cu)
+# ------------------------------------------------------------------------------------------------
+def vae_latent_in(z: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, inv_scale: float) -> torch.Tensor:
+    """z fp32 (B, C, H, W) -> fp16 NHWC [B*H*W, 64] = post_quant_conv(z * inv_scale), channels >= C zero."""
+    lib = _lib.load()
+    _req(z, torch.float32, "z")
+    _req(w, torch.float32, "w")
+    _req(bias, torch.float32, "bias")
+    B, Cc, H, W = z.shape
+    z = z.contiguous()
+    out = torch.empty((B * H * W, 64), dtype=HALF, device=z.device)
+    check(lib.idiff_vae_latent_in(z.data_ptr(), w.data_ptr(), bias.data_ptr(), float(inv_scale), out.data_ptr(), B, Cc,
+                                  H * W, _stream()), "idiff_vae_latent_in")
+    return out
+
+
+def softmax_rows_(x: torch.Tensor) -> torch.Tensor:
+    """In-place softmax over the last dimension of an fp16 [rows, n] matrix (fp32 arithmetic)."""
+    lib = _lib.load()
+    _req(x, HALF, "x")
+    rows, n = x.shape
+    check(_launch("softmax_rows", 0.0, 4.0 * x.numel(), lambda: lib.idiff_softmax_rows(
+        x.data_ptr(), rows, n, x.stride(0), _stream())), "idiff_softmax_rows")
+    return x

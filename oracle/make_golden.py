@@ -233,6 +233,31 @@ def gen_extra(ref, which):
         torch.save(out_s, path_s)
 
 
+def gen_vae(ref):
+    """First-stage model (tests/golden/vae.pt): the reference's AutoencoderKL (configs/test_*.yaml:42-61) with
+    the synthetic weights, decode of a seeded 32x32 latent (256^2 image) and the encoder moments of a 64^2 image."""
+    from ldm.models.autoencoder import AutoencoderKL
+    from instancediffusion_b200.weights import synth_tensor
+    with ref_harness.fast_init():
+        ae = AutoencoderKL(dict(torch_oracle.VAE_DDCONFIG), 4, torch_oracle.VAE_SCALE).eval()
+    ae.load_state_dict({k: synth_tensor("vae." + k, tuple(v.shape), cases.WEIGHT_SEED) for k, v in ae.state_dict().items()},
+                       strict=True)
+    out = {}
+    with torch.no_grad():
+        for name, spec in cases.VAE_CASES.items():
+            g = torch.Generator().manual_seed(spec["seed"])
+            if spec["kind"] == "decode":
+                z = torch.randn((spec["batch"], 4, spec["size"], spec["size"]), generator=g) * spec["std"]
+                t = time.time()
+                out[name] = ae.decode(z).float().contiguous()
+            else:
+                x = torch.randn((spec["batch"], 3, spec["size"], spec["size"]), generator=g) * spec["std"]
+                t = time.time()
+                out[name] = ae.quant_conv(ae.encoder(x)).float().contiguous()
+            print(f"  vae {name}: {time.time() - t:.1f}s shape={tuple(out[name].shape)} absmax={out[name].abs().max():.3f}")
+    torch.save(out, os.path.join(GOLDEN, "vae.pt"))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--threads", type=int, default=os.cpu_count())
@@ -255,6 +280,8 @@ def main():
         print("convnext cases"); gen_convnext(ref)
     if "unifusion_mask" in only:
         print("unifusion mask cases"); gen_unifusion_mask(ref)
+    if "vae" in only:
+        print("first-stage (VAE) cases"); gen_vae(ref)
     if any(o.startswith("unet_extra") or o.startswith("samplers_extra") for o in only):
         print("round-2 unet / sampler cases"); gen_extra(ref, only)
 

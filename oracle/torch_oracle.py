@@ -393,3 +393,75 @@ def plms_sample(eval_fn: Callable, inputs: List[dict], uc, S: int, guidance: flo
     for i in range(mis_step, total):
         step(inputs[0], olds[0], i)
     return inputs[0]["x"]
+
+
+# ------------------------------------------------------------------------------------------------
+# first-stage model: ldm/models/autoencoder.py, ldm/modules/diffusionmodules/model.py
+# ------------------------------------------------------------------------------------------------
+VAE_DDCONFIG = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
+                    ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)  # configs/test_*.yaml:47-61
+VAE_SCALE = 0.18215                                                                            # configs/test_*.yaml:45
+
+
+def _gn6(sd: SD, p: str, x):
+    return F.group_norm(x, 32, sd[p + ".weight"], sd[p + ".bias"], 1e-6)  # model.py:38-39
+
+
+def vae_resnet_block(sd: SD, p: str, x):
+    """ResnetBlock.forward with temb=None, model.py:119-141."""
+    h = F.conv2d(F.silu(_gn6(sd, p + ".norm1", x)), sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], padding=1)
+    h = F.conv2d(F.silu(_gn6(sd, p + ".norm2", h)), sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], padding=1)
+    if p + ".nin_shortcut.weight" in sd:
+        x = F.conv2d(x, sd[p + ".nin_shortcut.weight"], sd[p + ".nin_shortcut.bias"])
+    return x + h
+
+
+def vae_attn_block(sd: SD, p: str, x):
+    """AttnBlock.forward, model.py:177-202."""
+    h = _gn6(sd, p + ".norm", x)
+    q = F.conv2d(h, sd[p + ".q.weight"], sd[p + ".q.bias"])
+    k = F.conv2d(h, sd[p + ".k.weight"], sd[p + ".k.bias"])
+    v = F.conv2d(h, sd[p + ".v.weight"], sd[p + ".v.bias"])
+    b, c, hh, ww = q.shape
+    w_ = torch.bmm(q.reshape(b, c, hh * ww).permute(0, 2, 1), k.reshape(b, c, hh * ww)) * (int(c) ** (-0.5))
+    w_ = torch.softmax(w_, dim=2)
+    h = torch.bmm(v.reshape(b, c, hh * ww), w_.permute(0, 2, 1)).reshape(b, c, hh, ww)
+    return x + F.conv2d(h, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
+
+
+def vae_decode(sd: SD, z, cfg: dict = VAE_DDCONFIG, scale: float = VAE_SCALE):
+    """AutoencoderKL.decode (autoencoder.py:33-37) + Decoder.forward (model.py:528-569)."""
+    nres, nb = len(cfg["ch_mult"]), cfg["num_res_blocks"]
+    h = F.conv2d(z.float() / scale, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
+    d = "decoder"
+    h = F.conv2d(h, sd[d + ".conv_in.weight"], sd[d + ".conv_in.bias"], padding=1)
+    h = vae_resnet_block(sd, d + ".mid.block_1", h)
+    h = vae_attn_block(sd, d + ".mid.attn_1", h)
+    h = vae_resnet_block(sd, d + ".mid.block_2", h)
+    for lvl in reversed(range(nres)):
+        for i in range(nb + 1):
+            h = vae_resnet_block(sd, f"{d}.up.{lvl}.block.{i}", h)
+        if lvl != 0:
+            h = F.interpolate(h, scale_factor=2.0, mode="nearest")
+            h = F.conv2d(h, sd[f"{d}.up.{lvl}.upsample.conv.weight"], sd[f"{d}.up.{lvl}.upsample.conv.bias"], padding=1)
+    h = F.silu(_gn6(sd, d + ".norm_out", h))
+    return F.conv2d(h, sd[d + ".conv_out.weight"], sd[d + ".conv_out.bias"], padding=1)
+
+
+def vae_encode_moments(sd: SD, x, cfg: dict = VAE_DDCONFIG):
+    """quant_conv(Encoder.forward(x)) (autoencoder.py:27-29, model.py:429-459): the (mean | logvar) planes the
+    posterior is sampled from (the sample itself draws torch.randn, so parity is stated on the moments)."""
+    nres, nb = len(cfg["ch_mult"]), cfg["num_res_blocks"]
+    e = "encoder"
+    h = F.conv2d(x.float(), sd[e + ".conv_in.weight"], sd[e + ".conv_in.bias"], padding=1)
+    for lvl in range(nres):
+        for i in range(nb):
+            h = vae_resnet_block(sd, f"{e}.down.{lvl}.block.{i}", h)
+        if lvl != nres - 1:
+            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0)  # model.py:70-73
+            h = F.conv2d(h, sd[f"{e}.down.{lvl}.downsample.conv.weight"], sd[f"{e}.down.{lvl}.downsample.conv.bias"], stride=2)
+    h = vae_resnet_block(sd, e + ".mid.block_1", h)
+    h = vae_attn_block(sd, e + ".mid.attn_1", h)
+    h = vae_resnet_block(sd, e + ".mid.block_2", h)
+    h = F.conv2d(F.silu(_gn6(sd, e + ".norm_out", h)), sd[e + ".conv_out.weight"], sd[e + ".conv_out.bias"], padding=1)
+    return F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])

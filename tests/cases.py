@@ -101,6 +101,14 @@ SAMPLER_EXTRA_CASES = {
 }
 
 
+# first-stage model (ldm/models/autoencoder.py): latent std 0.9 is what a finished sampler run hands to decode
+VAE_CASES = {
+    "decode_32": dict(kind="decode", batch=1, size=32, seed=41, std=0.9),
+    "decode_b2_16": dict(kind="decode", batch=2, size=16, seed=42, std=0.9),
+    "encode_64": dict(kind="encode", batch=1, size=64, seed=43, std=0.5),
+}
+
+
 def build_inputs(name: str, spec: dict) -> Dict[str, torch.Tensor]:
     ins = {k: synth_input(name, k, shp) for k, shp in spec["inputs"].items()}
     if spec.get("same_kv"):

@@ -215,8 +215,8 @@ def imp(name):
         return None
 import ldm.modules.attention as A, instancediffusion_b200.ldm.modules.attention as B
 assert A is B
-ae = imp("ldm.models.autoencoder"); assert ae is not None and ae.__file__.startswith(root)
-dm = imp("ldm.modules.diffusionmodules.model"); assert dm is not None and dm.__file__.startswith(root)
+ae = imp("ldm.models.autoencoder"); assert ae is not None and ae.__name__.startswith("instancediffusion_b200.")
+dm = imp("ldm.modules.diffusionmodules.model"); assert dm is not None and dm.__name__.startswith("instancediffusion_b200.")
 assert dm.LinearAttention.__module__.endswith("ldm.modules.attention")   # served by the reference's own file
 imp("ldm.modules.encoders.modules")
 imp("utils.input"); imp("utils.checkpoint"); imp("dataset.decode_item")
@@ -226,7 +226,11 @@ ours = {"ldm.models.diffusion.ldm.LatentDiffusion", "ldm.modules.diffusionmodule
         "grounding_input.text_grounding_tokinzer_input.GroundingNetInput"}
 for t in ours:
     assert get_obj_from_str(t).__module__.startswith("instancediffusion_b200."), t
-assert get_obj_from_str("ldm.models.autoencoder.AutoencoderKL").__module__ == "ldm.models.autoencoder"
+# the first stage is mirrored too (AutoencoderKL.decode runs right after the sampler, inference.py:96) ...
+assert get_obj_from_str("ldm.models.autoencoder.AutoencoderKL").__module__.startswith("instancediffusion_b200.")
+import ldm.modules.diffusionmodules.model as vae_blocks
+assert vae_blocks.Decoder.__module__.startswith("instancediffusion_b200.")
+assert vae_blocks.LinAttnBlock.__module__.startswith("_idiff_reference_original.")  # not mirrored: the reference's own
 try:
     get_obj_from_str("ldm.modules.encoders.modules.FrozenCLIPEmbedder")
 except ImportError as e:
@@ -242,6 +246,13 @@ except ImportError as e:
     assert any(t in str(e) for t in THIRD), e
 dropin.uninstall()
 assert "ldm.modules.attention" not in sys.modules
+# ... unless asked not to: then the reference's own autoencoder keeps serving
+dropin.install(first_stage=False)
+try:
+    assert get_obj_from_str("ldm.models.autoencoder.AutoencoderKL").__module__ == "ldm.models.autoencoder"
+except ImportError as e:
+    assert (e.name or "").split(".")[0] in THIRD, e
+dropin.uninstall()
 print("ok")
 """ % (ref, ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd="/tmp")

@@ -229,3 +229,30 @@ def test_plms_sample_restatement_matches_reference(unet_sd, name):
     rel = _rel_l2(x, gold[name])
     print(f"[oracle plms_sample] {name}: rel_l2 {rel:.2e}")
     assert rel < 2e-4, rel
+
+
+# ------------------------------------------------------------------------------------------------
+# first-stage model (AutoencoderKL.decode / encoder moments)
+# ------------------------------------------------------------------------------------------------
+def _vae_sd():
+    from instancediffusion_b200.ldm.models.autoencoder import AutoencoderKL
+    with torch.device("meta"):
+        m = AutoencoderKL(dict(TO.VAE_DDCONFIG), 4, TO.VAE_SCALE)
+    return {k: synth_tensor("vae." + k, tuple(v.shape), cases.WEIGHT_SEED) for k, v in m.state_dict().items()}
+
+
+@pytest.mark.parametrize("name", list(cases.VAE_CASES))
+def test_vae_restatement_matches_reference(name):
+    """oracle vae_decode / vae_encode_moments vs the reference's AutoencoderKL (tests/golden/vae.pt)."""
+    gold = _load("vae.pt")
+    spec = cases.VAE_CASES[name]
+    sd = _vae_sd()
+    g = torch.Generator().manual_seed(spec["seed"])
+    with torch.no_grad():
+        if spec["kind"] == "decode":
+            z = torch.randn((spec["batch"], 4, spec["size"], spec["size"]), generator=g) * spec["std"]
+            got = TO.vae_decode(sd, z)
+        else:
+            x = torch.randn((spec["batch"], 3, spec["size"], spec["size"]), generator=g) * spec["std"]
+            got = TO.vae_encode_moments(sd, x)
+    _close(got, gold[name], 1e-4, 5e-5, f"vae {name}")

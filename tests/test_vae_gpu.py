@@ -1,0 +1,121 @@
+"""`-m gpu` parity of the first-stage model (AutoencoderKL.decode, the step right after the sampler loop;
+SURVEY.md section 8f-1) against the reference's own fp32 output (tests/golden/vae.pt, oracle/make_golden.py
+--only vae), plus the kernels that exist only for it.  The reference decodes in fp32 (inference.py:96 is
+outside the autocast region); here activations are fp16 with fp32 accumulation / statistics, so the bound is
+an fp16 one: relative L2 of the image, stated per test at <= 2x the value measured on the B200."""
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(HERE, "golden")
+
+
+def _load(name):
+    path = os.path.join(GOLDEN, name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} not generated")
+    return torch.load(path, map_location="cpu")
+
+
+@pytest.fixture(scope="module")
+def vae(cuda_device):
+    from oracle import torch_oracle as TO
+    from instancediffusion_b200.ldm.models.autoencoder import AutoencoderKL
+    from instancediffusion_b200.weights import synth_tensor
+    with torch.device("meta"):
+        m = AutoencoderKL(dict(TO.VAE_DDCONFIG), 4, TO.VAE_SCALE)
+    m = m.to_empty(device=cuda_device).eval()
+    m.load_state_dict({k: synth_tensor("vae." + k, tuple(v.shape), cases.WEIGHT_SEED) for k, v in m.state_dict().items()},
+                      strict=True)
+    return m
+
+
+def _rel(got, ref):
+    got = got.detach().float().cpu()
+    assert got.shape == ref.shape, (tuple(got.shape), tuple(ref.shape))
+    assert torch.isfinite(got).all()
+    return ((got - ref).norm() / ref.norm()).item(), ((got - ref).abs().max() / ref.abs().max()).item()
+
+
+@pytest.mark.parametrize("name", [n for n, s in cases.VAE_CASES.items() if s["kind"] == "decode"])
+def test_vae_decode_matches_reference_golden(cuda_device, vae, name):
+    gold = _load("vae.pt")
+    spec = cases.VAE_CASES[name]
+    g = torch.Generator().manual_seed(spec["seed"])
+    z = (torch.randn((spec["batch"], 4, spec["size"], spec["size"]), generator=g) * spec["std"]).to(cuda_device)
+    img = vae.decode(z)
+    rel, mx = _rel(img, gold[name])
+    print(f"[vae/{name}] rel_l2={rel:.3e} max_err/ref_max={mx:.3e}")
+    assert rel < 6e-3 and mx < 3e-2, (name, rel, mx)
+
+
+def test_vae_encoder_moments_match_reference_golden(cuda_device, vae):
+    gold = _load("vae.pt")
+    spec = cases.VAE_CASES["encode_64"]
+    g = torch.Generator().manual_seed(spec["seed"])
+    x = (torch.randn((spec["batch"], 3, spec["size"], spec["size"]), generator=g) * spec["std"]).to(cuda_device)
+    h = vae.encoder(x)
+    mom = torch.nn.functional.conv2d(h, vae.quant_conv.weight.float(), vae.quant_conv.bias.float())
+    rel, mx = _rel(mom, gold["encode_64"])
+    print(f"[vae/encode_64] rel_l2={rel:.3e} max_err/ref_max={mx:.3e}")
+    assert rel < 6e-3 and mx < 3e-2, (rel, mx)
+
+
+def test_vae_decode_512_image_vs_fp32_oracle(cuda_device, vae):
+    """The bench-size decode (64x64 latent -> 512x512 image, batch 2) against the plain-torch fp32 restatement of
+    the reference run on the same GPU (no golden at this size: 6 MB per image)."""
+    from oracle import torch_oracle as TO
+    sd = {k: v.detach().float() for k, v in vae.state_dict().items()}
+    g = torch.Generator().manual_seed(7)
+    z = (torch.randn((2, 4, 64, 64), generator=g) * 0.9).to(cuda_device)
+    img = vae.decode(z)
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ref = TO.vae_decode(sd, z).cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    rel, mx = _rel(img, ref)
+    print(f"[vae/decode_512] rel_l2={rel:.3e} max_err/ref_max={mx:.3e}")
+    assert rel < 6e-3 and mx < 3e-2, (rel, mx)
+
+
+def test_softmax_rows_and_latent_prologue(cuda_device):
+    from instancediffusion_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn((300, 4096), generator=g) * 3).to(cuda_device).half()
+    ref = torch.softmax(x.float(), dim=-1)
+    got = ops.softmax_rows_(x.clone()).float()
+    assert (got - ref).abs().max().item() < 2e-3 * ref.max().item() + 1e-6
+    assert (got.sum(-1) - 1).abs().max().item() < 2e-3
+    z = torch.randn((2, 4, 24, 40), generator=g).to(cuda_device)
+    w = torch.randn((4, 4), generator=g).to(cuda_device)
+    b = torch.randn((4,), generator=g).to(cuda_device)
+    out = ops.vae_latent_in(z, w, b, 1.0 / 0.18215).float().view(2, 24 * 40, 64)
+    ref = torch.einsum("oc,bchw->bhwo", w, z / 0.18215).reshape(2, -1, 4) + b
+    assert (out[..., :4] - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+    assert out[..., 4:].abs().max().item() == 0.0
+
+
+def test_im2col_s2_pad01(cuda_device):
+    """operand of the first-stage Downsample: F.pad(0,1,0,1) + conv3x3 stride 2 padding 0 (model.py:70-74)."""
+    import torch.nn.functional as F
+    from instancediffusion_b200 import ops
+    from instancediffusion_b200.packing import pack_conv3x3
+    g = torch.Generator().manual_seed(5)
+    B, H, W, Cc = 2, 12, 16, 64
+    x = torch.randn((B, Cc, H, W), generator=g).to(cuda_device)
+    wt = (torch.randn((64, Cc, 3, 3), generator=g) / 24).to(cuda_device)
+    x16 = x.permute(0, 2, 3, 1).reshape(B * H * W, Cc).half().contiguous()
+    cols = ops.im2col_s2(x16, B, H, W, pad01=True)
+    out = ops.gemm(cols, pack_conv3x3(wt.half())).float().view(B, H // 2, W // 2, 64).permute(0, 3, 1, 2)
+    ref = F.conv2d(F.pad(x.half().float(), (0, 1, 0, 1)), wt.half().float(), stride=2)
+    assert (out - ref).abs().max().item() < 4e-3 * ref.abs().max().item() + 2e-3

@@ -46,7 +46,8 @@ for name in sys.argv[1:]:
     mhz = ((t[:, 13] - t[:, 12]).float() / (t[:, 7] - t[:, 0]).float().clamp(min=1) * 1e3).median()
     print(f"== {name}: {t.shape[0]} CTAs, kernel span {rel[:, 7].max():.1f} us, SM clock during kernel ~{mhz:.0f} MHz")
     names[14] = "c0 tmem loaded"
-    for i, n in list(enumerate(names[:12])) + [(14, names[14])]:
+    names[15] = "c1 start"
+    for i, n in list(enumerate(names[:12])) + [(14, names[14]), (15, names[15])]:
         col = rel[:, i][t[:, i] > 0]
         if col.numel():
             print(f"   {n:16s} min {col.min():7.2f}  median {col.median():7.2f}  max {col.max():7.2f} us")
