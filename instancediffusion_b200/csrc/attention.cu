@@ -134,7 +134,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== UMMA issuer =====================
-    if (lane == 0) {
+    // all 32 lanes walk the (warp-uniform) schedule, one elected lane issues: the descriptors then live in
+    // uniform registers and the UMMAs of a product issue back to back (see gemm2.cu: as a single-lane loop every
+    // tcgen05.mma cost ~20 instructions of R2UR moves and an ELECT retry loop on the pacing thread)
+    {
       constexpr uint32_t idesc_qk = make_idesc_f16(BQ, BKV, 0, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(BQ, DV, 0, 0, /*B MN-major*/ 1);
       const uint32_t q_base = smem_u32(sQ);
@@ -145,15 +148,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
         const uint32_t k_base = smem_u32(sK + s * Cfg::KV_TILE_BYTES);
         const uint32_t d_tmem = tmem_base + ((j & 1) ? Cfg::TMEM_S1 : Cfg::TMEM_S0);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < Cfg::KSTEPS; ++kk) {
-          const uint64_t adesc =
-              make_smem_desc_sw128(q_base + (kk >> 2) * (BQ * 128) + (kk & 3) * 32, 16, 1024);
-          const uint64_t bdesc =
-              make_smem_desc_sw128(k_base + (kk >> 2) * (BKV * 128) + (kk & 3) * 32, 16, 1024);
-          umma_f16_ss(d_tmem, adesc, bdesc, idesc_qk, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < Cfg::KSTEPS; ++kk) {
+            const uint64_t adesc =
+                make_smem_desc_sw128(q_base + (kk >> 2) * (BQ * 128) + (kk & 3) * 32, 16, 1024);
+            const uint64_t bdesc =
+                make_smem_desc_sw128(k_base + (kk >> 2) * (BKV * 128) + (kk & 3) * 32, 16, 1024);
+            umma_f16_ss(d_tmem, adesc, bdesc, idesc_qk, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[j & 1]);
         }
-        umma_commit(&s_full[j & 1]);
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
@@ -164,17 +170,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_wait(&v_full[s], (j / STAGES) & 1);
         tc_fence_after();
         const uint32_t v_base = smem_u32(sV + s * Cfg::KV_TILE_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint64_t adesc =
-              make_smem_desc_sw128(p_base + (kk >> 2) * (BQ * 128) + (kk & 3) * 32, 16, 1024);
-          // V tile: [BKV keys][64 d] rows of 128 B per d-chunk = MN-major, 8-key atoms of 1024 B,
-          // next 64-wide d chunk BKV*128 B further on (LBO).
-          const uint64_t bdesc = make_smem_desc_sw128(v_base + kk * 2048, BKV * 128, 1024);
-          umma_f16_ss(tmem_base + Cfg::TMEM_O, adesc, bdesc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < BKV / 16; ++kk) {
+            const uint64_t adesc =
+                make_smem_desc_sw128(p_base + (kk >> 2) * (BQ * 128) + (kk & 3) * 32, 16, 1024);
+            // V tile: [BKV keys][64 d] rows of 128 B per d-chunk = MN-major, 8-key atoms of 1024 B,
+            // next 64-wide d chunk BKV*128 B further on (LBO).
+            const uint64_t bdesc = make_smem_desc_sw128(v_base + kk * 2048, BKV * 128, 1024);
+            umma_f16_ss(tmem_base + Cfg::TMEM_O, adesc, bdesc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&kv_empty[s]);
+          umma_commit(pv_done);
         }
-        umma_commit(&kv_empty[s]);
-        umma_commit(pv_done);
+        __syncwarp();
       }
     }
     __syncwarp();

@@ -270,12 +270,17 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== UMMA issuer =====================
-    if (lane == 0) {
+    // All 32 lanes walk the event loop with warp-uniform control flow (every barrier probe is made uniform
+    // by a vote) and ONE elected lane issues: as a single-lane loop the descriptors lived in vector registers
+    // and every tcgen05.mma cost ~10 instructions (R2UR moves + an ELECT retry loop) on the one thread whose
+    // instruction latency paces both Q tiles of the CTA -- 14 UMMAs, 4-5 commits and ~8 barrier probes per
+    // 64-key step.  Uniform, the UMMAs of a product issue back to back from uniform registers (gemm2.cu, same
+    // measurement).  Stage / phase of every ring are running counters (no div / mod by 3).
+    {
       constexpr uint32_t idesc_qk = make_idesc_f16(BQ, BKV, 0, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(BQ, C::DV, 0, 0, /*B MN-major*/ 1);
       // Every descriptor here shares its high word (SBO = 1024 B, version 1, SWIZZLE_128B); the low
       // word is (address >> 4) | (LBO >> 4) << 16, so stepping an operand by X bytes is lo += X >> 4.
-      // The issuing thread therefore spends one integer add per UMMA.
       constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
       constexpr uint32_t LBO_K = (16u >> 4) << 16;             // K-major operands (unused field)
       constexpr uint32_t LBO_V = ((BKV * 128u) >> 4) << 16;    // MN-major V: next 64-wide d chunk (unused)
@@ -293,54 +298,64 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(acc)
             : "memory");
       };
-      auto issue_qk = [&](int q, int n) {  // S[q] = Q_q . K(n)^T
-        const uint32_t q_lo = q_lo0 + q * (C::Q_BYTES >> 4);
-        const uint32_t k_lo = k_lo0 + (n % STAGES) * (C::KV_BYTES >> 4);
-        const uint32_t d_tmem = tmem_base + C::S_COL + q * 64;
-#pragma unroll
-        for (int kk = 0; kk < C::KSTEPS; ++kk)
-          umma_lo(d_tmem, q_lo + kk * 2, k_lo + kk * 2, idesc_qk, kk > 0 ? 1u : 0u);
-        umma_commit(&s_full[q]);
-      };
-      auto issue_pv = [&](int q, int n) {  // O[q] += P[q] . V(n)
-        const uint32_t v_lo = v_lo0 + (n % STAGES) * (C::KV_BYTES >> 4);
-        const uint32_t p_lo = p_lo0 + q * (C::P_BYTES >> 4);
-        const uint32_t o_tmem = tmem_base + C::O_COL + q * 64;
-        const uint32_t acc0 = n > 0 ? 1u : 0u;
-#pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk)
-          umma_lo(o_tmem, p_lo + kk * 2, v_lo + kk * (2048 >> 4), idesc_pv, kk > 0 ? 1u : acc0);
-        umma_commit(&pv_done[q]);
-      };
-      // Event-driven issue: each Q tile advances on its own barriers (S pulled into registers -> next
-      // Q.K^T, P written -> P.V).  Per tile the block indices only grow, and every test asks for the
-      // completion right after one this thread has already observed, so parities are unambiguous.
-      mbar_wait(q_full, 0);
+      // per Q tile: next block of Q.K^T / P.V, and the ring stage / phase of its K and V tiles
       int qk_n[2] = {0, 0}, pv_n[2] = {0, 0};
+      uint32_t qk_s[2] = {0, 0}, qk_ph[2] = {0, 0}, pv_s[2] = {0, 0}, pv_ph[2] = {0, 0};
+      mbar_wait(q_full, 0);
       long long t_idle = 0;
       while (pv_n[0] < T || pv_n[1] < T) {
         bool progress = false;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
+          // ---- S[q] = Q_q . K(n)^T once S[q] has been pulled into registers and K(n) has landed ----
           const int nq = qk_n[q];
-          if (nq < T && (nq == 0 || mbar_test(&s_free[q], (nq - 1) & 1)) &&
-              mbar_test(&k_full[nq % STAGES], (nq / STAGES) & 1)) {
+          bool go = false;
+          if (nq < T) go = (nq == 0 || mbar_test(&s_free[q], (nq - 1) & 1)) && mbar_test(&k_full[qk_s[q]], qk_ph[q]);
+          if (__any_sync(0xffffffffu, go)) {  // completion is monotonic: any lane's observation holds for all
             tc_fence_after();
-            if (nq >= 16 && nq < 24) stamp(128 + (q * 8 + nq - 16) * 4 + 0);
-            issue_qk(q, nq);
-            if (nq >= 16 && nq < 24) stamp(128 + (q * 8 + nq - 16) * 4 + 1);
+            if (TRACE && lane == 0 && nq >= 16 && nq < 24) stamp(128 + (q * 8 + nq - 16) * 4 + 0);
+            if (elect_one()) {
+              const uint32_t q_lo = q_lo0 + q * (C::Q_BYTES >> 4);
+              const uint32_t k_lo = k_lo0 + qk_s[q] * (C::KV_BYTES >> 4);
+              const uint32_t d_tmem = tmem_base + C::S_COL + q * 64;
+#pragma unroll
+              for (int kk = 0; kk < C::KSTEPS; ++kk) umma_lo(d_tmem, q_lo + kk * 2, k_lo + kk * 2, idesc_qk, kk > 0 ? 1u : 0u);
+              umma_commit(&s_full[q]);
+            }
+            __syncwarp();
+            if (TRACE && lane == 0 && nq >= 16 && nq < 24) stamp(128 + (q * 8 + nq - 16) * 4 + 1);
             qk_n[q] = nq + 1;
+            if (++qk_s[q] == STAGES) {
+              qk_s[q] = 0;
+              qk_ph[q] ^= 1;
+            }
             progress = true;
           }
+          // ---- O[q] += P[q] . V(n) once P[q] is in shared memory and V(n) has landed ----
           const int np = pv_n[q];
-          if (np < qk_n[q] && mbar_test(&p_full[q], np & 1) &&
-              mbar_test(&v_full[np % STAGES], (np / STAGES) & 1)) {
+          go = false;
+          if (np < qk_n[q]) go = mbar_test(&p_full[q], np & 1) && mbar_test(&v_full[pv_s[q]], pv_ph[q]);
+          if (__any_sync(0xffffffffu, go)) {
             tc_fence_after();
-            if (np >= 16 && np < 24) stamp(128 + (q * 8 + np - 16) * 4 + 2);
-            issue_pv(q, np);
-            if (np >= 16 && np < 24) stamp(128 + (q * 8 + np - 16) * 4 + 3);
+            if (TRACE && lane == 0 && np >= 16 && np < 24) stamp(128 + (q * 8 + np - 16) * 4 + 2);
+            if (elect_one()) {
+              const uint32_t v_lo = v_lo0 + pv_s[q] * (C::KV_BYTES >> 4);
+              const uint32_t p_lo = p_lo0 + q * (C::P_BYTES >> 4);
+              const uint32_t o_tmem = tmem_base + C::O_COL + q * 64;
+              const uint32_t acc0 = np > 0 ? 1u : 0u;
+#pragma unroll
+              for (int kk = 0; kk < BKV / 16; ++kk)
+                umma_lo(o_tmem, p_lo + kk * 2, v_lo + kk * (2048 >> 4), idesc_pv, kk > 0 ? 1u : acc0);
+              umma_commit(&pv_done[q]);
+              if (pv_n[q ^ 1] > np) umma_commit(&kv_empty[pv_s[q]]);  // both tiles are past block np
+            }
+            __syncwarp();
+            if (TRACE && lane == 0 && np >= 16 && np < 24) stamp(128 + (q * 8 + np - 16) * 4 + 3);
             pv_n[q] = np + 1;
-            if (pv_n[q ^ 1] > np) umma_commit(&kv_empty[np % STAGES]);  // both tiles are past block np
+            if (++pv_s[q] == STAGES) {
+              pv_s[q] = 0;
+              pv_ph[q] ^= 1;
+            }
             progress = true;
           }
         }
@@ -349,8 +364,9 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         } else {  // bounded like mbar_wait: a protocol bug traps instead of hanging the GPU
           if (t_idle == 0) t_idle = clock64();
           else if (clock64() - t_idle > 8000000000LL) {
-            printf("idiff: attention2 issue loop stalled block=(%d,%d,%d) qk=(%d,%d) pv=(%d,%d)\n", blockIdx.x,
-                   blockIdx.y, blockIdx.z, qk_n[0], qk_n[1], pv_n[0], pv_n[1]);
+            if (lane == 0)
+              printf("idiff: attention2 issue loop stalled block=(%d,%d,%d) qk=(%d,%d) pv=(%d,%d)\n", blockIdx.x,
+                     blockIdx.y, blockIdx.z, qk_n[0], qk_n[1], pv_n[0], pv_n[1]);
             __trap();
           }
         }

@@ -77,13 +77,14 @@ struct Params {
 // 16-byte global access per thread and row (which costs an L1 transaction per access: measured
 // ~0.7 us per chunk, tools/trace_gemm.py).  The staging buffer takes smem from the operand ring,
 // so it is used for the short-K layers (epilogue-bound); long-K convolutions keep the deep ring.
-template <int BN, bool TMA_EPI, int EW = 8>
+template <int BN, bool TMA_EPI, int EW = 8, int CG = 1>
 struct Cfg {
+  static_assert(CG == 1 || CG == 2, "cta_group 1 or 2");
   static constexpr int THREADS = 128 + EW * 32;
   static constexpr int PARTS = EW / 4;            // column parts of a tile (one epilogue warp per quarter and part)
   static constexpr int NCHT = BN / CHUNK;         // 16-column accumulator chunks of a tile
   static constexpr int NCH_MAX = (NCHT + PARTS - 1) / PARTS;  // ... owned by one warp, at most
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;  // cta_group::2: each CTA of the pair stages half of B
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int BOX_BYTES = 32 * CHUNK * 2;                       // 1 KiB
   // TMA epilogue staging: one [32 rows x BN/2 columns] fp16 box per epilogue warp (row-major, no swizzle):
@@ -328,12 +329,18 @@ constexpr int MODE_PLAIN = 0;  // bias / row-add table, optional SiLU, optional 
 constexpr int MODE_GEGLU = 1;  // (value + b) * gelu(gate + b), fp16 out with N/2 columns
 constexpr int MODE_NCHW = 2;   // fp32 (B, N, HW) output (the final conv -> eps)
 
-template <int BN, int MODE, bool TMA_EPI, int EW, bool REALLOC = true>
+// CG = 2: the kernel runs as clusters of two CTAs (one TPC) that share each UMMA: tcgen05.mma.cta_group::2 with
+// M = 256 -- every CTA stages its own 128 A rows and HALF of the B tile, the tensor cores of both SMs read both
+// halves.  Measured (tools/r2_probe2.py, profiles/README.md round 2): the 1-CTA SS-mode UMMA is bound by its
+// shared-memory operand fetch at ~64 B/clk (128 x 256 x 16: 12 KB = 192 clk against 128 clk of math; 128 x 160:
+// 9 KB = 144 against 80), not by issue, TMA or L2; halving B per SM brings 256-wide tiles to the math rate.
+// The leader CTA (cluster rank 0) issues; the peer forwards its "operands landed" barrier phases.
+template <int BN, int MODE, bool TMA_EPI, int EW, int CG = 1, bool REALLOC = true>
 __global__ void __launch_bounds__(128 + EW * 32, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
              const Params p) {
-  using C = Cfg<BN, TMA_EPI, EW>;
+  using C = Cfg<BN, TMA_EPI, EW, CG>;
   constexpr int STAGES = C::STAGES;
   constexpr int EPI_WARPS = EW;
   extern __shared__ uint8_t smem_raw[];
@@ -347,13 +354,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
   uint64_t* res_bar = bars + 2 * STAGES + 4;     // [EPI_WARPS] residual boxes landed (TMA_EPI)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + MAX_EPI_WARPS);
+  uint64_t* peer_full = bars + 2 * STAGES + 4 + MAX_EPI_WARPS;  // [STAGES] (CG 2, leader): the peer's operands landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4 + MAX_EPI_WARPS);
   float* s_epi = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES + C::BAR_BYTES);  // [2][EPI_TAB_PB][BN]
   uint8_t* s_stage = smem + STAGES * C::STAGE_BYTES + C::BAR_BYTES + C::TAB_BYTES;          // [quarter][NCHT][1 KiB]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int cta = blockIdx.x;
+  uint32_t crank = 0;  // rank in the CTA pair
+  if constexpr (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int cta = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // index in the work schedule (pair / CTA)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -364,8 +374,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], EPI_WARPS * 32);
+      mbar_init(&tmem_empty[a], CG * EPI_WARPS * 32);  // (CG 2: the leader's barrier also counts the peer's epilogue)
     }
+    for (int s = 0; s < STAGES; ++s) mbar_init(&peer_full[s], 1);
     for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&res_bar[w], 1);
     if (TMA_EPI) {
       tma_prefetch_desc(&tmO);
@@ -373,9 +384,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_cg2<C::TMEM_COLS>(tmem_slot);  // collective over the pair: same columns in both SMs
+    else tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync();  // barriers of BOTH CTAs are initialised before any remote arrive / commit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();  // the next kernel's prologue may overlap this kernel (host.cuh launch_pdl)
@@ -384,17 +399,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (p.trace) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      p.trace[(long)cta * 16 + slot] = t;
+      p.trace[(long)blockIdx.x * 16 + slot] = t;
     }
   };
   if (threadIdx.x == 0) {
     stamp(0);
-    if (p.trace) p.trace[(long)cta * 16 + 12] = (unsigned long long)clock64();  // SM clock at entry
+    if (p.trace) p.trace[(long)blockIdx.x * 16 + 12] = (unsigned long long)clock64();  // SM clock at entry
   }
 
   auto tile_origin = [&](int tile, int& n0, int& m0, int& b0, int& h0, int& w0) {
     const int n_tile = tile % p.n_tiles;
-    const int m_tile = tile / p.n_tiles;
+    const int m_tile = (CG == 2) ? 2 * (tile / p.n_tiles) + (int)crank : tile / p.n_tiles;  // pair tile = 2 stacked M tiles
     n0 = n_tile * BN;
     m0 = m_tile * BM;
     b0 = h0 = w0 = 0;
@@ -421,58 +436,130 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       WorkIter it(p, cta);
       Seg sg;
-      uint32_t kc = 0;  // running k-block counter over all segments (ring position)
+      uint32_t s = 0, ph = 0;  // ring position: running stage / phase (no div / mod on the refill path: every clock
+                               // between "stage released" and "TMA issued" is part of the ring's turnaround)
       while (it.next(sg)) {
         int n0, m0, b0, h0, w0;
         tile_origin(sg.tile, n0, m0, b0, h0, w0);
-        for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++kc) {
-          const int s = kc % STAGES;
-          const uint32_t ph = (kc / STAGES) & 1;
+        const int nb = n0 + (int)crank * (BN / CG) * (CG - 1);  // CG 2: this CTA's half of the B tile
+        // conv: k-block kb = (tap, 64-channel slice cb); walked incrementally
+        int tap = 0, cb = 0, ky = 0, kx = 0;
+        if (p.conv) {
+          tap = sg.kb0 / p.kb_per_tap;
+          cb = sg.kb0 - tap * p.kb_per_tap;
+          ky = tap / 3;
+          kx = tap - ky * 3;
+        }
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
           if (p.conv) {
-            const int tap = kb / p.kb_per_tap;
-            const int cb = kb - tap * p.kb_per_tap;
-            const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], cb * BK, w0 + kx - 1,
-                        h0 + ky - 1, b0);
+            tma_load_4d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], cb * BK, w0 + kx - 1, h0 + ky - 1, b0);
+            if (++cb == p.kb_per_tap) {
+              cb = 0;
+              if (++kx == 3) {
+                kx = 0;
+                ++ky;
+              }
+            }
           } else {
             tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BK, m0);
           }
-          tma_load_2d(sB + s * C::B_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+          tma_load_2d(sB + s * C::B_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, nb);
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== UMMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0, 0);
+    // All 32 lanes walk the (warp-uniform) schedule and ONE elected lane issues: with a single-lane loop
+    // ptxas kept the descriptors in vector registers and paid ~25 instructions (5 R2UR + an ELECT retry loop)
+    // per UMMA; this way they live in uniform registers and the four UMMAs of a k-block issue back to back
+    // (UTCHMMA x4, UTCBAR).  Descriptors = (low word + constant high word), one add per UMMA; running
+    // stage / phase instead of div / mod.
+    constexpr uint32_t idesc = make_idesc_f16(BM * CG, BN, 0, 0, 0);
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B, version 1, SWIZZLE_128B
+    const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);  // LBO (unused, swizzled K-major) = 16 B
+    const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+    auto umma_lo = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+      if constexpr (CG == 2) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(d_tmem),
+            "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(acc)
+            : "memory");
+      } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(d_tmem),
+            "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(acc)
+            : "memory");
+      }
+    };
+    auto commit = [&](uint64_t* bar) {  // CG 2: the arrival lands on the barrier at this offset in BOTH CTAs
+      if constexpr (CG == 2) umma_commit_cg2(bar);
+      else umma_commit(bar);
+    };
+    if (CG == 1 || crank == 0) {
       WorkIter it(p, cta);
       Seg sg;
-      uint32_t kc = 0, sc = 0;
+      uint32_t sc = 0, s = 0, ph = 0;
+      bool first = true;
       while (it.next(sg)) {
         const int acc = sc & 1;
-        mbar_wait(&tmem_empty[acc], ((sc >> 1) & 1) ^ 1);
+        if constexpr (CG == 2) mbar_wait_cluster(&tmem_empty[acc], ((sc >> 1) & 1) ^ 1);
+        else mbar_wait(&tmem_empty[acc], ((sc >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
-        for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++kc) {
-          const int s = kc % STAGES;
-          mbar_wait(&full_bar[s], (kc / STAGES) & 1);
-          if (kc == 0) stamp(1);
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          if constexpr (CG == 2) mbar_wait_cluster(&peer_full[s], ph);
+          if (first && lane == 0) stamp(1);
+          first = false;
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + s * A_STAGE_BYTES);
-          const uint32_t b_base = smem_u32(sB + s * C::B_STAGE_BYTES);
+          const uint32_t a_lo = a_lo0 + s * (A_STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + s * (C::B_STAGE_BYTES >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(a_base + k * 32, 16, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > sg.kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) umma_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, (kb > sg.kb0 || k > 0) ? 1u : 0u);
+            commit(&empty_bar[s]);
           }
-          umma_commit(&empty_bar[s]);
+          __syncwarp();
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
         }
-        umma_commit(&tmem_full[acc]);
-        if (sc == 0) stamp(2);
+        if (elect_one()) commit(&tmem_full[acc]);
+        __syncwarp();
+        if (sc == 0 && lane == 0) stamp(2);
         ++sc;
+      }
+    } else {
+      // CG 2, peer CTA: tell the leader when this CTA's operands of each stage have landed
+      if (lane == 0) {
+        WorkIter it(p, cta);
+        Seg sg;
+        uint32_t s = 0, ph = 0;
+        while (it.next(sg)) {
+          for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+            mbar_wait(&full_bar[s], ph);
+            mbar_arrive_remote(&peer_full[s], 0);
+            if (++s == STAGES) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
       }
     }
     __syncwarp();
@@ -656,7 +743,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                         __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])));
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty[acc]);
+        mbar_arrive(&tmem_empty[acc]);  // (stream-K is never scheduled for CTA pairs)
         // __syncwarp orders the lanes' partial stores before lane 0's release store (cumulative), so a
         // single release replaces 32 per-thread __threadfence() (MEMBAR.GPU + L1 invalidate each).
         __syncwarp();
@@ -1067,7 +1154,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           __stcg(p.ln_out + (long)((sg.tile % p.n_tiles) * PARTS + part) * p.M + out_row, make_float2(ln_ps, ln_pq));
         if (sc == 0 && threadIdx.x == 128) stamp(5);
         tc_fence_before();
-        mbar_arrive(&tmem_empty[acc]);
+        if (CG == 2 && crank != 0) mbar_arrive_remote(&tmem_empty[acc], 0);  // the leader's issuer waits for both epilogues
+        else mbar_arrive(&tmem_empty[acc]);
         if (fixup) {
           // consume the followers' flags so the next launch (or graph replay) starts clean
           __syncwarp();
@@ -1081,14 +1169,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (TMA_EPI && warp >= 4 && lane == 0) tma_store_wait_read();  // boxes must outlive their stores
   if (threadIdx.x == 128) stamp(6);
-  __syncthreads();
+  if constexpr (CG == 2) {
+    tc_fence_before();
+    cluster_sync();  // no CTA of the pair leaves (or frees tensor memory) while the other may still signal / read it
+  } else {
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     stamp(7);
-    if (p.trace) p.trace[(long)cta * 16 + 13] = (unsigned long long)clock64();  // SM clock at exit
+    if (p.trace) p.trace[(long)blockIdx.x * 16 + 13] = (unsigned long long)clock64();  // SM clock at exit
   }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_cg2<C::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -1115,9 +1209,10 @@ static void choose_patch(int H, int W, int* PW, int* PH, int* PB) {
   *PB = 128 / (pw * ph);
 }
 
-template <int BN, int MODE, bool TMA_EPI, int EW = 8, bool REALLOC = true>
+template <int BN, int MODE, bool TMA_EPI, int CG = 1>
 static int launch(const idiff_gemm_args* a, cudaStream_t stream, bool want_sk) {
-  using C = Cfg<BN, TMA_EPI, EW>;
+  constexpr int EW = 8;
+  using C = Cfg<BN, TMA_EPI, EW, CG>;
   Params p;
   memset(&p, 0, sizeof(p));
   p.M = a->M;
@@ -1173,11 +1268,11 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream, bool want_sk) {
   {
     const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     const uint64_t strides[1] = {(uint64_t)a->ldw * 2};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(BN / CG)};  // CG 2: each CTA of the pair loads half of the N tile
     if (encode_tmap_f16(&tmB, a->w, 2, dims, strides, box)) return -1;
   }
   p.n_tiles = (a->N + BN - 1) / BN;
-  p.T = p.n_tiles * m_tiles;
+  p.T = p.n_tiles * ((m_tiles + CG - 1) / CG);  // CG 2: a work item is a pair of stacked M tiles
 
   if (g_num_sms == 0) {
     int dev = 0;
@@ -1191,7 +1286,8 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream, bool want_sk) {
   // takes precedence over the process-wide default of idiff_set_gemm_workspace
   void* ws_ptr = a->workspace ? a->workspace : g_ws;
   const long ws_bytes = a->workspace ? a->workspace_bytes : g_ws_bytes;
-  const bool use_sk = want_sk && ws_ptr && ws_bytes >= ws_need && p.KB >= 8 && (p.T % g_num_sms) != 0 &&
+  const int workers = g_num_sms / CG;  // CTAs, or CTA pairs (one per TPC)
+  const bool use_sk = CG == 1 && want_sk && ws_ptr && ws_bytes >= ws_need && p.KB >= 8 && (p.T % g_num_sms) != 0 &&
                       (long)p.T * p.KB >= g_num_sms;
   if (use_sk) {
     p.G = g_num_sms;
@@ -1201,7 +1297,7 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream, bool want_sk) {
     p.sflags = reinterpret_cast<int*>(ws_ptr);
     p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws_ptr) + kFlagBytes);
   } else {
-    p.G = g_num_sms < p.T ? g_num_sms : p.T;
+    p.G = workers < p.T ? workers : p.T;
     p.T_dp = p.T;
     p.U_sk = 0;
   }
@@ -1231,11 +1327,12 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream, bool want_sk) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MODE, TMA_EPI, EW, REALLOC>,
+    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MODE, TMA_EPI, EW, CG>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  IDIFF_CHECK_CUDA(launch_pdl(gemm2_kernel<BN, MODE, TMA_EPI, EW, REALLOC>, dim3(p.G), dim3(C::THREADS), C::SMEM_BYTES, stream, tmA, tmB, tmO, tmR, p));
+  IDIFF_CHECK_CUDA(launch_pdl_cluster(gemm2_kernel<BN, MODE, TMA_EPI, EW, CG>, dim3(p.G * CG), dim3(C::THREADS), C::SMEM_BYTES,
+                                      stream, CG, tmA, tmB, tmO, tmR, p));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1319,43 +1416,62 @@ static Plan plan_gemm(const idiff_gemm_args* a, int fixed_bn) {  // fixed_bn: 0 
 }
 
 struct Resolved {
-  int bn, mode, ew;
+  int bn, mode, ew, cg;
   bool tma_epi, sk;
 };
+
+// CTA pairs (cta_group::2) or single CTAs?  Measured on the B200 (tools/bench_kernels.py, profiles/README.md round 2):
+// the pair kernel is correct at every shape (IDIFF_GEMM_CG=2 runs the whole kernel suite) and its k-block is ~11 %
+// cheaper (conv 320->320 @64: 917 vs 1035 clk), but it runs plain rounds of 256-row work items over 74 TPCs without
+// stream-K and loses that again to tile quantisation (84 vs 82 us); tools/micro/umma_bench2.cu shows why the k-block
+// does not reach the 4 x N/2 clk of math in either mode: the two-barrier operand ring has a ~2700 clk turnaround
+// (commit -> empty barrier -> producer -> full barrier -> issuer), which six 36 KB stages of N = 160 do not cover.
+// Single CTAs stay the default; IDIFF_GEMM_CG=2 selects pairs for every eligible GEMM (A/B runs).
+static int choose_cg(const idiff_gemm_args* a, int bn, bool sk1) {
+  (void)a; (void)bn; (void)sk1;
+  static const int forced = []() {
+    const char* e = getenv("IDIFF_GEMM_CG");
+    return e ? atoi(e) : 0;
+  }();
+  return forced == 2 ? 2 : 1;
+}
+
 static Resolved resolve(const idiff_gemm_args* a) {
   Resolved r;
   // GEGLU: one 256-column accumulator tile = 128 value columns + their 128 gates (packing.py)
   if (a->flags & IDIFF_EPI_GEGLU) {
-    r = {256, MODE_GEGLU, 8, true, plan_gemm(a, 256).sk};
+    const bool sk = plan_gemm(a, 256).sk;
+    r = {256, MODE_GEGLU, 8, choose_cg(a, 256, sk), true, sk};
     return r;
   }
   if (a->flags & IDIFF_OUT_F32_NCHW) {
-    r = {128, MODE_NCHW, 8, false, plan_gemm(a, 128).sk};
+    r = {128, MODE_NCHW, 8, 1, false, plan_gemm(a, 128).sk};
     return r;
   }
   // short K: the epilogue dominates -> TMA-staged epilogue (shallower operand ring);
   // long K (3x3 convolutions): deep operand ring, direct epilogue hidden behind the next mainloop
   const bool tma_epi = ((a->K + BK - 1) / BK) <= kTmaEpiMaxKB;
   const Plan pl = plan_gemm(a, false);
-  r = {pl.bn, MODE_PLAIN, 8, tma_epi, pl.sk};
+  r = {pl.bn, MODE_PLAIN, 8, choose_cg(a, pl.bn, pl.sk), tma_epi, pl.sk};
   return r;
 }
 
 template <int BN>
 static int launch_plain(const Resolved& r, const idiff_gemm_args* a, cudaStream_t stream) {
-  if (!r.tma_epi) return launch<BN, MODE_PLAIN, false, 8>(a, stream, r.sk);
-  return launch<BN, MODE_PLAIN, true, 8>(a, stream, r.sk);
+  if (r.cg == 2) return r.tma_epi ? launch<BN, MODE_PLAIN, true, 2>(a, stream, false) : launch<BN, MODE_PLAIN, false, 2>(a, stream, false);
+  return r.tma_epi ? launch<BN, MODE_PLAIN, true, 1>(a, stream, r.sk) : launch<BN, MODE_PLAIN, false, 1>(a, stream, r.sk);
 }
 
-// One instantiation per (tile width, epilogue mode): each kernel carries only its own mode's code (an
+// One instantiation per (tile width, epilogue mode, cta_group): each kernel carries only its own mode's code (an
 // all-modes kernel was ~140 KB of SASS and stalled on instruction fetch: 26 % stall_no_inst, profiles/).
 // The epilogue-warp count is a template parameter of the kernel; 12 and 16 warps (three / four column parts,
 // 152 / 104 registers) were measured SLOWER than 8 at every UNet shape (profiles/README.md, round 2: qkv C320
 // 41 -> 45 -> 66 us) and are not instantiated.
 int gemm_v2(const idiff_gemm_args* a, cudaStream_t stream) {
   const Resolved r = resolve(a);
-  if (r.mode == MODE_GEGLU) return launch<256, MODE_GEGLU, true, 8>(a, stream, r.sk);
-  if (r.mode == MODE_NCHW) return launch<128, MODE_NCHW, false, 8>(a, stream, r.sk);
+  if (r.mode == MODE_GEGLU)
+    return r.cg == 2 ? launch<256, MODE_GEGLU, true, 2>(a, stream, false) : launch<256, MODE_GEGLU, true, 1>(a, stream, r.sk);
+  if (r.mode == MODE_NCHW) return launch<128, MODE_NCHW, false, 1>(a, stream, r.sk);
   switch (r.bn) {
     case 256: return launch_plain<256>(r, a, stream);
     case 192: return launch_plain<192>(r, a, stream);
