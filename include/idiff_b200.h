@@ -114,6 +114,12 @@ typedef struct {
   int nq, n0, n1;             /* n1 may be 0 */
   int kv1_batch;              /* 1: segment 1 shared by all batch entries; else == batch */
   float scale;                /* head_dim^-0.5 (attention.py:102,164) */
+  /* Instance-isolation mask of the gated self-attention at the 64x64 level (attention.py:187-255; live with
+     efficient_attention=False, eval_local.py --use_masked_att): NULL, or uint32 words -- query i may attend key j
+     iff (mask_q[b*nq + i] & mask_k[b*(n0+n1) + j]) != 0, or j is visual token i itself (the reference adds 1e-9
+     on the diagonal).  idiff_attmask_words builds them from the (B, 30, 64, 64) att_masks. head_dim 40 only. */
+  const void* mask_q;
+  const void* mask_k;
 } idiff_attn_args;
 int idiff_attention(const idiff_attn_args* args, void* stream);
 
@@ -192,6 +198,24 @@ int idiff_plms_update(const float* x, const float* e_c, const float* e_u, float 
                       float* e_out, float* x_out, long n, void* stream);
 /* out = mean over `count` latents given as an array of device pointers (plms_instance.py:135) */
 int idiff_latent_mean(const float* const* xs_dev, int count, float* out, long n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Instance-isolation attention mask, host prep on the GPU
+ * ------------------------------------------------------------------------------------------- */
+/* utils/input.py:34-37,79 (get_attmask_w_box): att_masks[b, k, x1:x2, y1:y2] = 1 for every instance k < counts[b]
+   with x1 = rint(box[0] * size) ... (numpy round-half-even, in double); boxes fp32 (B, max_objs, 4) xyxy in [0,1],
+   att_masks fp32 (B, max_objs, size, size) fully written (zeros elsewhere).  Note the reference indexes the FIRST
+   spatial axis with x: kept as is. */
+int idiff_boxes_to_attmask(const float* boxes, const int* counts, float* att_masks, int batch, int max_objs, int size,
+                           void* stream);
+/* attention.py:203-247 as bit words: att_masks fp32 (B, n_objs <= 30, P) with P = size*size visual tokens ->
+   mask_q uint32 [B][P]       = (bits k: att_masks[b,k,p] > 0) | bit 31
+   mask_k uint32 [B][P + 4*n_objs + tail]: visual p: the same bits without bit 31; object tokens in the order
+   [box | point | scribble | mask] (text_grounding_net.py:291-300): box / mask token k -> bit k, point / scribble
+   tokens and the `tail` trailing tokens -> bit 31 (attend / attended by everything).
+   A batch entry with active[b] == 0 (all-zero masks or drop_box_mask: attention.py:201) gets all-ones words. */
+int idiff_attmask_words(const float* att_masks, const int* active, void* mask_q, void* mask_k, int batch, int n_objs,
+                        int pixels, int tail, void* stream);
 
 /* timestep_embedding (util.py:160-180): out fp16 [B, dim] = [cos(t*f) | sin(t*f)],
    f_k = exp(-ln(1e4)*k/(dim/2)) */

@@ -39,6 +39,7 @@ class AttnArgs(C.Structure):
         ("batch", C.c_int), ("heads", C.c_int), ("head_dim", C.c_int),
         ("nq", C.c_int), ("n0", C.c_int), ("n1", C.c_int), ("kv1_batch", C.c_int),
         ("scale", C.c_float),
+        ("mask_q", C.c_void_p), ("mask_k", C.c_void_p),
     ]
 
 
@@ -78,6 +79,8 @@ SIGNATURES = {
     "idiff_patchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "idiff_dwconv7x7": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "idiff_seg_tokens": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "idiff_boxes_to_attmask": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "idiff_attmask_words": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "idiff_vae_latent_in": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp]),
     "idiff_softmax_rows": (_i, [_vp, _i, _i, _l, _vp]),
 }

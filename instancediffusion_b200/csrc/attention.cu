@@ -363,6 +363,14 @@ extern "C" int idiff_attention(const idiff_attn_args* a, void* stream) {
   IDIFF_REQUIRE(a->out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
                 "idiff_attention: out must be 16B aligned, out_ld %% 8 == 0");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a->mask_q || a->mask_k) {
+    IDIFF_REQUIRE(a->mask_q && a->mask_k, "idiff_attention: mask_q and mask_k come together");
+    IDIFF_REQUIRE(a->head_dim == 40, "idiff_attention: the instance-isolation mask exists at the 64x64 level only "
+                                     "(head_dim 40; attention.py:197), got head_dim %d", a->head_dim);
+    IDIFF_REQUIRE(a->n0 % 4 == 0 && (a->n0 + a->n1) % 4 == 0 && (reinterpret_cast<uintptr_t>(a->mask_k) & 15) == 0,
+                  "idiff_attention: mask_k must be 16B aligned with n0 and n0 + n1 multiples of 4");
+    return att2::attention_v2_d40(a, s);
+  }
   switch (a->head_dim) {
     case 40: {
       // attention2.cu (two Q tiles, f16x2 exponentials, tensor-core row sums) is the production

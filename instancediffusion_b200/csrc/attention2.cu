@@ -37,6 +37,10 @@ struct Params {
   float scale_log2e;
   __half* out;
   int out_ld;
+  // instance-isolation mask of the gated self-attention (attention.py:187-255): query i may attend key j iff
+  // (mask_q[b][i] & mask_k[b][j]) != 0, or j is the visual token i itself (the reference's 1e-9 diagonal)
+  const uint32_t* mask_q;  // [batch][nq]
+  const uint32_t* mask_k;  // [batch][n0 + n1]
 };
 
 template <int D>
@@ -179,7 +183,8 @@ IDIFF_DEVICE float exp_block(const uint32_t (&sv)[2][32], float c, float mc, uin
 // TRACE (IDIFF_ATT2_TRACE=1): one CTA records clock stamps of blocks 16..23 in shared memory and prints
 // them at exit -- a timeline of the hand-offs that costs the measured kernel nothing but a few STS.
 // POLY: bit u of the mask = pair u (mod 8) of every 8 score pairs takes the FMA-pipe exp2 instead of MUFU.
-template <int D, bool TRACE = false, uint32_t POLY = 0>
+// MASKED: the instance-isolation mask of Params::mask_q / mask_k is applied to the scores.
+template <int D, bool TRACE = false, uint32_t POLY = 0, bool MASKED = false>
 __global__ void __launch_bounds__(THREADS, 2)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                   const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
@@ -389,6 +394,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
     float m_used = -INFINITY;  // maximum the exponent is taken against (raw score units)
     float l = 0.0f;            // running row sum of exp
+    uint32_t qword = 0xffffffffu;
+    if (MASKED) {
+      const int qrow_m = q0 + q * BQ + r;
+      qword = qrow_m < p.nq ? __ldg(p.mask_q + (long)b * p.nq + qrow_m) : 0xffffffffu;
+    }
 
     for (int j = 0; j < T; ++j) {
       const bool tr = TRACE && r == 0 && j >= 16 && j < 24;
@@ -413,6 +423,23 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int jj = 0; jj < BKV; ++jj)
           if (jj >= nv) sv[jj >> 5][jj & 31] = 0xff800000u;
       }
+      if (MASKED) {
+        // the 64 key words of this block (the same for every thread: L1 broadcast) against this row's word
+        const int key0 = (seg1 ? p.n0 + (j - T0) * BKV : j * BKV);
+        const uint4* kw = reinterpret_cast<const uint4*>(p.mask_k + (long)b * (p.n0 + p.n1) + key0);
+        const int self_jj = seg1 ? -1 : (q0 + q * BQ + r) - key0;  // this row's own key, if it lies in the block
+#pragma unroll
+        for (int g = 0; g < BKV / 4; ++g) {
+          uint4 w = make_uint4(0, 0, 0, 0);
+          if (4 * g < nv) w = __ldg(kw + g);  // (n0 and n1 blocks start 4-word aligned: n0 % 4 == 0 is required)
+          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int jj = 4 * g + e;
+            if ((ww[e] & qword) == 0u && jj != self_jj) sv[jj >> 5][jj & 31] = 0xff800000u;
+          }
+        }
+      }
       float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
       for (int jj = 0; jj < 32; jj += 4) {  // 3-input max: two scores per issue slot
@@ -424,11 +451,13 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const float m_blk = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       // lazy maximum: only move the reference when it grew by more than 8 in the exp2 domain
       float alpha = 1.0f;
-      if ((m_blk - m_used) * c > 8.0f) {
+      if (m_blk > m_used && (m_blk - m_used) * c > 8.0f) {
         alpha = exp2_approx((m_used - m_blk) * c);  // first block: 2^-inf = 0 (l = 0, O is not read)
         m_used = m_blk;
       }
-      const float mc = m_used * c;
+      // (MASKED: a block may be dead for a row before the row has seen any live key: m_used is still -inf and the
+      // scores are all -inf; exponent against 0 then gives P = 0 instead of NaN)
+      const float mc = (MASKED && m_used == -INFINITY) ? 0.0f : m_used * c;
       if (tr) stamp(tb + 3);
       // ---- exponentials, packed to fp16 in place; row sum in fp32 ----
       // Packed fp32x2 arithmetic for the exponent argument and the row sum (one issue slot per two scores);
@@ -557,6 +586,8 @@ int attention_v2_d40(const idiff_attn_args* a, cudaStream_t stream) {
   p.scale_log2e = a->scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__half*>(a->out);
   p.out_ld = a->out_ld;
+  p.mask_q = reinterpret_cast<const uint32_t*>(a->mask_q);
+  p.mask_k = reinterpret_cast<const uint32_t*>(a->mask_k);
   static const bool trace = getenv("IDIFF_ATT2_TRACE") != nullptr;
   // share of the exponentials taken on the FMA pipe: pairs per 8 (IDIFF_ATT2_POLY=0..4, tuning knob)
   static const int poly = []() {
@@ -564,18 +595,20 @@ int attention_v2_d40(const idiff_attn_args* a, cudaStream_t stream) {
     const int v = e ? atoi(e) : 2;  // measured (B200, batch 8, 4096 keys): 0: 420, 2: 408, 3: 430, 4: 456 us
     return (v >= 0 && v <= 4) ? v : 2;
   }();
-  auto kern = trace ? attention2_kernel<D, true, 0u>
+  const bool masked = a->mask_q != nullptr;
+  auto kern = masked ? attention2_kernel<D, false, 0u, true>
+              : trace ? attention2_kernel<D, true, 0u>
               : poly == 0 ? attention2_kernel<D, false, 0u>
               : poly == 1 ? attention2_kernel<D, false, 0x10u>
               : poly == 2 ? attention2_kernel<D, false, 0x22u>
               : poly == 3 ? attention2_kernel<D, false, 0x4Au>
                           : attention2_kernel<D, false, 0xAAu>;
   const int smem_bytes = C::SMEM_BYTES + (trace ? C::TRACE_BYTES : 0);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[2] = {false, false};  // (per masked / unmasked kernel; the env knobs are read once)
+  if (!attr_set[masked]) {
     IDIFF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     IDIFF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;  // (`kern` is fixed for the life of the process: both knobs are read once)
+    attr_set[masked] = true;
   }
   dim3 grid((a->nq + 2 * BQ - 1) / (2 * BQ), a->heads, a->batch);
   IDIFF_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), smem_bytes, stream, tmQ, tmK0, tmV0, tmK1, tmV1, p));

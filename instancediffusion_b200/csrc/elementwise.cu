@@ -207,6 +207,63 @@ static inline int grid_for(long total, int threads) {
   return (int)g;
 }
 
+// ---------------------------------------------------------------------------------------------
+// instance-isolation attention mask (utils/input.py:34-37, attention.py:203-247)
+// ---------------------------------------------------------------------------------------------
+// one thread per (b, k, a, c) element of att_masks
+__global__ void boxes_to_attmask_kernel(const float* __restrict__ boxes, const int* __restrict__ counts,
+                                        float* __restrict__ att, int B, int K, int S) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long total = (long)B * K * S * S;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % S);
+    long t = i / S;
+    const int a = (int)(t % S);
+    t /= S;
+    const int k = (int)(t % K);
+    const int b = (int)(t / K);
+    float v = 0.f;
+    if (k < counts[b]) {
+      const float* bx = boxes + ((long)b * K + k) * 4;
+      // int(np.round(box * image_size)): round half to even, computed in double like numpy on python floats
+      const int x1 = (int)rint((double)bx[0] * S), y1 = (int)rint((double)bx[1] * S);
+      const int x2 = (int)rint((double)bx[2] * S), y2 = (int)rint((double)bx[3] * S);
+      if (a >= x1 && a < x2 && c >= y1 && c < y2) v = 1.f;  // att_masks[idx][x1:x2, y1:y2] = 1 (x on the first axis)
+    }
+    att[i] = v;
+  }
+}
+
+// one thread per (b, token): token < P visual, then 4*K object tokens, then `tail`
+__global__ void attmask_words_kernel(const float* __restrict__ att, const int* __restrict__ active,
+                                     uint32_t* __restrict__ mq, uint32_t* __restrict__ mk, int B, int K, int P, int tail) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int NK = P + 4 * K + tail;
+  const long total = (long)B * NK;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / NK);
+    const int t = (int)(i - (long)b * NK);
+    uint32_t w;
+    if (!active[b]) {
+      w = 0xffffffffu;
+      if (t < P) mq[(long)b * P + t] = w;
+    } else if (t < P) {
+      w = 0;
+      for (int k = 0; k < K; ++k)
+        if (att[((long)b * K + k) * P + t] > 0.f) w |= 1u << k;
+      mq[(long)b * P + t] = w | 0x80000000u;
+    } else if (t < P + 4 * K) {
+      const int g = (t - P) / K, k = (t - P) - g * K;
+      w = (g == 0 || g == 3) ? (1u << k) : 0x80000000u;  // [box | point | scribble | mask]: only box and mask tokens are masked
+    } else {
+      w = 0x80000000u;
+    }
+    mk[i] = w;
+  }
+}
+
 }  // namespace idiff
 
 using namespace idiff;
@@ -298,6 +355,30 @@ extern "C" int idiff_latent_mean(const float* const* xs_dev, int count, float* o
 extern "C" int idiff_silu_f16(const void* x, void* y, long n, void* stream) {
   IDIFF_REQUIRE(x && y && n > 0, "idiff_silu_f16: bad arguments");
   IDIFF_CHECK_CUDA(launch_pdl(silu_f16_kernel, dim3(grid_for(n, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),  reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), n));
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int idiff_boxes_to_attmask(const float* boxes, const int* counts, float* att_masks, int batch, int max_objs,
+                                      int size, void* stream) {
+  using namespace idiff;
+  IDIFF_REQUIRE(boxes && counts && att_masks && batch > 0 && max_objs > 0 && size > 0, "idiff_boxes_to_attmask: bad arguments");
+  const long total = (long)batch * max_objs * size * size;
+  IDIFF_CHECK_CUDA(launch_pdl(boxes_to_attmask_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                              boxes, counts, att_masks, batch, max_objs, size));
+  IDIFF_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int idiff_attmask_words(const float* att_masks, const int* active, void* mask_q, void* mask_k, int batch,
+                                   int n_objs, int pixels, int tail, void* stream) {
+  using namespace idiff;
+  IDIFF_REQUIRE(att_masks && active && mask_q && mask_k, "idiff_attmask_words: null pointer argument");
+  IDIFF_REQUIRE(n_objs > 0 && n_objs <= 30 && pixels > 0 && tail >= 0, "idiff_attmask_words: 1..30 instances supported (got %d)", n_objs);
+  const long total = (long)batch * (pixels + 4 * n_objs + tail);
+  IDIFF_CHECK_CUDA(launch_pdl(attmask_words_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                              att_masks, active, reinterpret_cast<uint32_t*>(mask_q), reinterpret_cast<uint32_t*>(mask_k), batch,
+                              n_objs, pixels, tail));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

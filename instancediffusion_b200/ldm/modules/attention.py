@@ -179,7 +179,7 @@ class SelfAttention(PackedModule):
         return ops.gemm(x16, wkv)
 
     def _fwd(self, x16, B, N, residual=None, gate=1.0, extra_kv=None, n_extra=0, extra_batch=0, out=None, ln=None,
-             want_stats=False):
+             want_stats=False, mask=None):
         """x16: normalised tokens [B*N, C] -- or, with ln=(RowStats, LnFold), the un-normalised stream.
         extra_kv: [Be*n_extra, 2C] additional keys/values (the object tokens of the gated block)."""
         p = self.pk()
@@ -192,6 +192,8 @@ class SelfAttention(PackedModule):
         kw = {}
         if extra_kv is not None:
             kw = dict(k1=extra_kv[:, :C], v1=extra_kv[:, C:2 * C], n1=n_extra, kv1_batch=extra_batch)
+        if mask is not None:  # instance-isolation mask words (attention.py:187-255; ops.attmask_words)
+            kw["mask"] = mask
         a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], batch=B, heads=self.heads,
                           head_dim=self.dim_head, nq=N, n0=N, scale=self.scale, **kw)
         return ops.gemm(a, p["wo"], p["bo"], residual=residual, gate=gate, out=out, want_stats=want_stats)
@@ -238,15 +240,20 @@ class GatedSelfAttentionDense(PackedModule):
         o = ops.layernorm(o, p["g1"], p["b1"], self.norm1.eps)
         return self.attn.project_kv(o)
 
-    def _fwd(self, x16, stats, B, N, obj_kv, n_obj, obj_batch):
+    def mask_applies(self, N: int, n_obj: int, n_inst: int) -> bool:
+        """attention.py:190-199: the instance-isolation mask is built only without `efficient_attention` and only
+        where the visual tokens are the 64x64 grid (N + n_obj - 4 * n_inst - 64 == 64 * 64)."""
+        return (not self.attn.efficient_attention) and N + n_obj - 4 * n_inst - 64 == 64 * 64
+
+    def _fwd(self, x16, stats, B, N, obj_kv, n_obj, obj_batch, mask=None):
         """In-place on x16 (the residual stream; `stats` = its RowStats).  Returns (x16, stats).  Identity
-        when scale == 0 (the alpha=0 steps)."""
+        when scale == 0 (the alpha=0 steps).  mask: (mask_q, mask_k) words of ops.attmask_words or None."""
         if self.scale == 0:
             return x16, stats
         p = self.pk()
         x16, stats = self.attn._fwd(x16, B, N, residual=x16, gate=float(self.scale) * p["tanh_attn"],
                                     extra_kv=obj_kv, n_extra=n_obj, extra_batch=obj_batch, out=x16,
-                                    ln=(stats, p["qkv"]), want_stats=True)
+                                    ln=(stats, p["qkv"]), want_stats=True, mask=mask)
         return self.ff._fwd(x16, residual=x16, gate=float(self.scale) * p["tanh_dense"], out=x16,
                             ln=(stats, p["ff"]), want_stats=True)
 
@@ -254,8 +261,26 @@ class GatedSelfAttentionDense(PackedModule):
         x16, B, N = to_tokens(x)
         o16, Bo, n_obj = to_tokens(objs)
         x16 = x16.clone()
-        y, _ = self._fwd(x16, ops.row_stats(x16), B, N, self.project_objs(o16), n_obj, Bo)
+        mask = attention_mask_words(self, grounding_input, drop_box_mask, B, N, n_obj)
+        y, _ = self._fwd(x16, ops.row_stats(x16), B, N, self.project_objs(o16), n_obj, Bo, mask=mask)
         return y.view(B, N, -1).to(x.dtype)
+
+
+def attention_mask_words(fuser: "GatedSelfAttentionDense", grounding_input, drop_box_mask, B, N, n_obj):
+    """attention.py:187-255 as the bit words of ops.attmask_words, or None when the reference builds no mask:
+    no `att_masks` in the grounding input, `efficient_attention`, another resolution than 64x64, all-zero masks
+    or dropped boxes (:201).  One device->host read of the mask sum (the reference does the same, :201)."""
+    if grounding_input is None or "att_masks" not in grounding_input:
+        return None
+    att = grounding_input["att_masks"]
+    n_inst = att.shape[1]
+    if not fuser.mask_applies(N, n_obj, n_inst):
+        return None
+    if drop_box_mask or not bool((att.sum() > 0).item()):
+        return None
+    active = torch.ones((B,), dtype=torch.int32, device=att.device)
+    return ops.attmask_words(att.float().expand(B, -1, -1, -1) if att.shape[0] != B else att.float(), active,
+                             tail=n_obj - 4 * n_inst)
 
 
 class BasicTransformerBlock(PackedModule):
@@ -284,11 +309,12 @@ class BasicTransformerBlock(PackedModule):
             "ff": self.ff.net[0].fold(self.norm3),
         }
 
-    def _fwd(self, x16, stats, B, N, ctx_kv, M, obj_kv, n_obj, obj_batch):
-        """x16: the residual stream (updated in place), stats: its RowStats (from the GEMM that wrote it)."""
+    def _fwd(self, x16, stats, B, N, ctx_kv, M, obj_kv, n_obj, obj_batch, mask=None):
+        """x16: the residual stream (updated in place), stats: its RowStats (from the GEMM that wrote it).
+        mask: instance-isolation mask words for the fuser (64x64 level, efficient_attention=False) or None."""
         p = self.pk()
         x16, stats = self.attn1._fwd(x16, B, N, residual=x16, out=x16, ln=(stats, p["qkv1"]), want_stats=True)
-        x16, stats = self.fuser._fwd(x16, stats, B, N, obj_kv, n_obj, obj_batch)
+        x16, stats = self.fuser._fwd(x16, stats, B, N, obj_kv, n_obj, obj_batch, mask=mask)
         x16, stats = self.attn2._fwd(x16, ctx_kv, B, N, M, residual=x16, out=x16, ln=(stats, p["q2"]), want_stats=True)
         return self.ff._fwd(x16, residual=x16, out=x16, ln=(stats, p["ff"]))
 
@@ -301,7 +327,8 @@ class BasicTransformerBlock(PackedModule):
         o16, Bo, n_obj = to_tokens(objs)
         obj_kv = self.fuser.project_objs(o16) if self.fuser.scale != 0 else None
         x16 = x16.clone()
-        y = self._fwd(x16, ops.row_stats(x16), B, N, self.attn2.project_kv(c16), M, obj_kv, n_obj, Bo)
+        mask = attention_mask_words(self.fuser, grounding_input, drop_box_mask, B, N, n_obj)
+        y = self._fwd(x16, ops.row_stats(x16), B, N, self.attn2.project_kv(c16), M, obj_kv, n_obj, Bo, mask=mask)
         return y.view(B, N, -1).to(x.dtype)
 
 
@@ -334,15 +361,16 @@ class SpatialTransformer(PackedModule):
             "w_out": pack_conv1x1(w16(self.proj_out.weight)), "b_out": f32(self.proj_out.bias),
         }
 
-    def _fwd(self, x16, B, H, W, ctx_kvs, M, obj_kvs, n_obj, obj_batch):
-        """x16 fp16 [B*H*W, C].  ctx_kvs / obj_kvs: one entry per transformer block."""
+    def _fwd(self, x16, B, H, W, ctx_kvs, M, obj_kvs, n_obj, obj_batch, mask=None):
+        """x16 fp16 [B*H*W, C].  ctx_kvs / obj_kvs: one entry per transformer block.  mask: see BasicTransformerBlock."""
         p = self.pk()
         n = ops.groupnorm(x16, p["gn_g"], p["gn_b"], batch=B, hw=H * W, groups=32, eps=self.norm.eps, silu=False)
         t, stats = ops.gemm(n, p["w_in"], p["b_in"], want_stats=True)
         for i, blk in enumerate(self.transformer_blocks):
             if i > 0:  # (depth > 1: the previous block's FF out-projection did not keep statistics)
                 stats = ops.row_stats(t)
-            t = blk._fwd(t, stats, B, H * W, ctx_kvs[i], M, obj_kvs[i] if obj_kvs is not None else None, n_obj, obj_batch)
+            t = blk._fwd(t, stats, B, H * W, ctx_kvs[i], M, obj_kvs[i] if obj_kvs is not None else None, n_obj, obj_batch,
+                         mask=mask if H * W == 64 * 64 else None)
         return ops.gemm(t, p["w_out"], p["b_out"], residual=x16)
 
     def forward(self, x, context, objs, grounding_input=None, drop_box_mask=False):
@@ -351,5 +379,6 @@ class SpatialTransformer(PackedModule):
         o16, Bo, n_obj = to_tokens(objs)
         ctx_kvs = [blk.attn2.project_kv(c16) for blk in self.transformer_blocks]
         obj_kvs = [blk.fuser.project_objs(o16) if blk.fuser.scale != 0 else None for blk in self.transformer_blocks]
-        y = self._fwd(x16, B, H, W, ctx_kvs, M, obj_kvs, n_obj, Bo)
+        mask = attention_mask_words(self.transformer_blocks[0].fuser, grounding_input, drop_box_mask, B, H * W, n_obj)
+        y = self._fwd(x16, B, H, W, ctx_kvs, M, obj_kvs, n_obj, Bo, mask=mask)
         return nhwc16_to_nchw(y, B, H, W, x.dtype)

@@ -28,7 +28,7 @@ from .... import ops
 from ....packing import pack_conv1x1, pack_conv3x3
 from ...util import instantiate_from_config
 from .._base import HALF, PackedModule, f32, nchw_to_nhwc16, nhwc16_to_nchw, w16
-from ..attention import SpatialTransformer
+from ..attention import SpatialTransformer, attention_mask_words
 from .util import zero_module
 
 
@@ -462,9 +462,11 @@ class UNetModel(PackedModule):
         self._ctx_cache[key] = (context, kv)  # keep `context` alive so the key stays unique
         return kv
 
-    def object_kv(self, grounding_input: Optional[dict]) -> Tuple[List[torch.Tensor], int, int]:
-        """UniFusion tokens -> per-fuser K|V ([Bo*184, 2C] each), cached per grounding_input dict.
-        `None` selects the null (CFG-uncond) tokens, which are a pure function of the weights."""
+    def object_kv(self, grounding_input: Optional[dict]):
+        """UniFusion tokens -> (per-fuser K|V ([Bo*184, 2C] each), Bo, n_obj, mask words or None), cached per
+        grounding_input dict.  `None` selects the null (CFG-uncond) tokens, which are a pure function of the
+        weights.  Mask words: the instance-isolation mask of the 64x64-level fusers (attention.py:187-255) when the
+        grounding input carries `att_masks` and the model was built without `efficient_attention`."""
         if grounding_input is None:
             gti = self.grounding_tokenizer_input
             gi = gti.get_null_input()
@@ -474,16 +476,18 @@ class UNetModel(PackedModule):
         else:
             gi = grounding_input
             key = tuple(self._tkey(gi[k]) for k in ("boxes", "masks", "positive_embeddings", "scribbles",
-                                                   "polygons", "segs", "points") if gi.get(k) is not None)
+                                                   "polygons", "segs", "points", "att_masks") if gi.get(k) is not None)
         hit = self._obj_cache.get(key)
         if hit is not None:
             return hit[1]
-        objs16, Bo, n_obj, _ = self.position_net._tokens(gi["boxes"], gi["masks"], gi["positive_embeddings"],
-                                                        gi["scribbles"], gi["polygons"], gi["segs"], gi["points"])
-        kvs = [blk.fuser.project_objs(objs16) for st in self._transformers() for blk in st.transformer_blocks]
+        objs16, Bo, n_obj, drop_box_mask = self.position_net._tokens(gi["boxes"], gi["masks"], gi["positive_embeddings"],
+                                                                    gi["scribbles"], gi["polygons"], gi["segs"], gi["points"])
+        blocks = [blk for st in self._transformers() for blk in st.transformer_blocks]
+        kvs = [blk.fuser.project_objs(objs16) for blk in blocks]
+        mask = attention_mask_words(blocks[0].fuser, gi, drop_box_mask, Bo, 64 * 64, n_obj)
         if len(self._obj_cache) > 64:
             self._obj_cache.clear()
-        val = (kvs, Bo, n_obj)
+        val = (kvs, Bo, n_obj, mask)
         self._obj_cache[key] = (gi, val)
         return val
 
@@ -499,7 +503,7 @@ class UNetModel(PackedModule):
         return any(blk.fuser.scale != 0 for st in self._transformers() for blk in st.transformer_blocks)
 
     def _core(self, x: torch.Tensor, t: torch.Tensor, ctx_kv_all: torch.Tensor, M: int,
-              obj_kvs: Optional[List[torch.Tensor]], n_obj: int) -> torch.Tensor:
+              obj_kvs: Optional[List[torch.Tensor]], n_obj: int, mask=None) -> torch.Tensor:
         """x fp32 (B,4,H,W), t fp32 (B,), ctx_kv_all fp16 [B*M, sumKV], obj_kvs per-fuser [B*n_obj, 2C]
         (or None on alpha=0 steps) -> eps fp32 (B,4,H,W)."""
         p = self.pk()
@@ -523,7 +527,7 @@ class UNetModel(PackedModule):
                 ctx_kvs.append(ctx_kv_all[:, a:b])
                 okvs.append(obj_kvs[blk_idx[0]] if obj_kvs is not None else None)
                 blk_idx[0] += 1
-            return st._fwd(h, B, hh, ww, ctx_kvs, M, okvs if obj_kvs is not None else None, n_obj, B)
+            return st._fwd(h, B, hh, ww, ctx_kvs, M, okvs if obj_kvs is not None else None, n_obj, B, mask=mask)
 
         def run_block(seq, h, hh, ww):
             for layer in seq:
@@ -569,7 +573,7 @@ class UNetModel(PackedModule):
 
     def _gather_inputs(self, inputs: List[dict]):
         """Concatenate independent forwards (cond / uncond / MIS trajectories) along the batch."""
-        xs, ts, ctxs, okv_lists = [], [], [], []
+        xs, ts, ctxs, okv_lists, masks = [], [], [], [], []
         active = self._fusers_active()
         n_obj = 0
         for inp in inputs:
@@ -580,7 +584,8 @@ class UNetModel(PackedModule):
                       else inp["timesteps"].float())
             ctxs.append(self.context_kv(inp["context"]))
             if active:
-                kvs, Bo, n_obj_i = self.object_kv(inp.get("grounding_input"))
+                kvs, Bo, n_obj_i, mask_i = self.object_kv(inp.get("grounding_input"))
+                masks.append((mask_i, b))
                 if n_obj and n_obj_i != n_obj:
                     raise ValueError(f"inputs of one batched forward carry different object-token counts "
                                      f"({n_obj} vs {n_obj_i}); prepare() them with the same max_box")
@@ -591,36 +596,50 @@ class UNetModel(PackedModule):
                     kvs = [kv.view(1, n_obj, -1).expand(b, n_obj, kv.shape[-1]).reshape(b * n_obj, -1) for kv in kvs]
                 okv_lists.append(kvs)
         M = inputs[0]["context"].shape[1]
+        # instance-isolation mask words: inputs without a mask (the CFG null branch) get all-ones words
+        mask = None
+        if any(m is not None for m, _ in masks):
+            dev = xs[0].device
+            mqs, mks = [], []
+            for m, b in masks:
+                if m is None:
+                    mqs.append(torch.full((b, 64 * 64), -1, dtype=torch.int32, device=dev))
+                    mks.append(torch.full((b, 64 * 64 + n_obj), -1, dtype=torch.int32, device=dev))
+                else:
+                    mq, mk = m
+                    mqs.append(mq if mq.shape[0] == b else mq.expand(b, -1))
+                    mks.append(mk if mk.shape[0] == b else mk.expand(b, -1))
+            mask = (torch.cat(mqs, 0).contiguous(), torch.cat(mks, 0).contiguous())
         if len(inputs) == 1:
-            return xs[0].contiguous(), ts[0].contiguous(), ctxs[0], M, (okv_lists[0] if active else None), n_obj
+            return xs[0].contiguous(), ts[0].contiguous(), ctxs[0], M, (okv_lists[0] if active else None), n_obj, mask
         x = torch.cat(xs, 0)
         t = torch.cat(ts, 0)
         ctx = torch.cat(ctxs, 0)
         okv = [torch.cat([l[i] for l in okv_lists], 0) for i in range(len(okv_lists[0]))] if active else None
-        return x, t, ctx, M, okv, n_obj
+        return x, t, ctx, M, okv, n_obj, mask
 
     @torch.no_grad()
     def forward_batched(self, inputs: List[dict]) -> List[torch.Tensor]:
         """Run several independent forwards as one batch; returns one eps tensor per input."""
-        x, t, ctx, M, okv, n_obj = self._gather_inputs(inputs)
-        eps = self._run_core(x, t, ctx, M, okv, n_obj)
+        x, t, ctx, M, okv, n_obj, mask = self._gather_inputs(inputs)
+        eps = self._run_core(x, t, ctx, M, okv, n_obj, mask)
         sizes = [inp["x"].shape[0] for inp in inputs]
         return list(torch.split(eps, sizes, 0))
 
-    def _run_core(self, x, t, ctx, M, okv, n_obj):
+    def _run_core(self, x, t, ctx, M, okv, n_obj, mask=None):
         if not self.use_cuda_graph:
-            return self._core(x, t, ctx, M, okv, n_obj)
+            return self._core(x, t, ctx, M, okv, n_obj, mask)
         # the fuser gates scale*tanh(alpha) are kernel arguments, frozen into a captured graph: the
         # per-fuser scales (set_alpha_scale may set any value, alpha_generator's decay stage is
         # fractional) are part of the key
         scales = tuple(float(blk.fuser.scale) for st in self._transformers() for blk in st.transformer_blocks) \
             if okv is not None else ()
-        key = (tuple(x.shape), M, scales, n_obj, getattr(self, "_first_conv_restored", False))
+        key = (tuple(x.shape), M, scales, n_obj, mask is not None, getattr(self, "_first_conv_restored", False))
         g = self._graphs.get(key)
         if g is None:
-            g = _CoreGraph(self, x, t, ctx, M, okv, n_obj)
+            g = _CoreGraph(self, x, t, ctx, M, okv, n_obj, mask)
             self._graphs[key] = g
-        return g.replay(x, t, ctx, okv)
+        return g.replay(x, t, ctx, okv, mask)
 
     def forward_single_input(self, input):
         return self.forward_batched([input])[0]
@@ -633,11 +652,12 @@ class _CoreGraph:
     """One captured CUDA graph of UNetModel._core for a fixed (batch, shapes, fuser on/off) key.
     Inputs are copied into static buffers, the graph is replayed, the static output is cloned."""
 
-    def __init__(self, model: UNetModel, x, t, ctx, M, okv, n_obj):
+    def __init__(self, model: UNetModel, x, t, ctx, M, okv, n_obj, mask=None):
         self.x = x.clone()
         self.t = t.clone()
         self.ctx = ctx.clone()
         self.okv = [o.clone() for o in okv] if okv is not None else None
+        self.mask = (mask[0].clone(), mask[1].clone()) if mask is not None else None
         model.pk()  # make sure packing (allocations + host work) happens outside capture
         for st in model._transformers():
             st.pk()
@@ -653,18 +673,21 @@ class _CoreGraph:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                model._core(self.x, self.t, self.ctx, M, self.okv, n_obj)
+                model._core(self.x, self.t, self.ctx, M, self.okv, n_obj, self.mask)
             torch.cuda.current_stream().wait_stream(s)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self.out = model._core(self.x, self.t, self.ctx, M, self.okv, n_obj)
+                self.out = model._core(self.x, self.t, self.ctx, M, self.okv, n_obj, self.mask)
 
-    def replay(self, x, t, ctx, okv):
+    def replay(self, x, t, ctx, okv, mask=None):
         self.x.copy_(x)
         self.t.copy_(t)
         self.ctx.copy_(ctx)
         if self.okv is not None:
             for dst, src in zip(self.okv, okv):
                 dst.copy_(src)
+        if self.mask is not None:
+            self.mask[0].copy_(mask[0])
+            self.mask[1].copy_(mask[1])
         self.graph.replay()
         return self.out.clone()

@@ -243,9 +243,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 def attention(q: torch.Tensor, k0: torch.Tensor, v0: torch.Tensor, *, batch: int, heads: int,
               head_dim: int, nq: int, n0: int, scale: float,
               k1: Optional[torch.Tensor] = None, v1: Optional[torch.Tensor] = None, n1: int = 0,
-              kv1_batch: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              kv1_batch: int = 0, out: Optional[torch.Tensor] = None,
+              mask: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
     """softmax(q k^T scale) v over segment 0 (+ optional segment 1) keys.  q/k/v are 2-D fp16 views
-    [batch*rows, >= heads*head_dim] (row stride = .stride(0)); returns fp16 [batch*nq, heads*head_dim]."""
+    [batch*rows, >= heads*head_dim] (row stride = .stride(0)); returns fp16 [batch*nq, heads*head_dim].
+    mask = (mask_q int32 [batch, nq], mask_k int32 [batch, n0 + n1]) from attmask_words: the instance-isolation
+    mask of the gated self-attention (head_dim 40 only)."""
     lib = _lib.load()
     for name, t in (("q", q), ("k0", k0), ("v0", v0)):
         _req(t, HALF, name)
@@ -266,6 +269,14 @@ def attention(q: torch.Tensor, k0: torch.Tensor, v0: torch.Tensor, *, batch: int
     a.nq, a.n0, a.n1 = nq, n0, n1
     a.kv1_batch = kv1_batch if kv1_batch else batch
     a.scale = float(scale)
+    if mask is not None:
+        mq, mk = mask
+        _req(mq, torch.int32, "mask_q")
+        _req(mk, torch.int32, "mask_k")
+        if tuple(mq.shape) != (batch, nq) or tuple(mk.shape) != (batch, n0 + n1) or not (mq.is_contiguous() and mk.is_contiguous()):
+            raise _lib.IdiffError(f"attention: mask shapes {tuple(mq.shape)} / {tuple(mk.shape)} do not match "
+                                  f"(batch {batch}, nq {nq}, keys {n0 + n1})")
+        a.mask_q, a.mask_k = mq.data_ptr(), mk.data_ptr()
     flops = 4.0 * batch * heads * nq * (n0 + n1) * head_dim
     nbytes = 2.0 * batch * C_ * (2 * nq + 2 * (n0 + n1))
     check(_launch(f"attention_d{head_dim}", flops, nbytes, lambda: lib.idiff_attention(C.byref(a), _stream())),
@@ -510,3 +521,36 @@ def softmax_rows_(x: torch.Tensor) -> torch.Tensor:
     check(_launch("softmax_rows", 0.0, 4.0 * x.numel(), lambda: lib.idiff_softmax_rows(
         x.data_ptr(), rows, n, x.stride(0), _stream())), "idiff_softmax_rows")
     return x
+
+
+# ------------------------------------------------------------------------------------------------
+# instance-isolation attention mask (utils/input.py:34-37, attention.py:203-247)
+# ------------------------------------------------------------------------------------------------
+def boxes_to_attmask(boxes: torch.Tensor, counts: torch.Tensor, size: int = 64) -> torch.Tensor:
+    """boxes fp32 (B, max_objs, 4) xyxy in [0, 1], counts int32 (B,) instances per sample -> att_masks fp32
+    (B, max_objs, size, size) exactly as utils/input.py:34-37 rasterises them on the host."""
+    lib = _lib.load()
+    _req(boxes, torch.float32, "boxes")
+    _req(counts, torch.int32, "counts")
+    B, K, _ = boxes.shape
+    boxes = boxes.contiguous()
+    att = torch.empty((B, K, size, size), dtype=torch.float32, device=boxes.device)
+    check(lib.idiff_boxes_to_attmask(boxes.data_ptr(), counts.data_ptr(), att.data_ptr(), B, K, size, _stream()),
+          "idiff_boxes_to_attmask")
+    return att
+
+
+def attmask_words(att_masks: torch.Tensor, active: torch.Tensor, tail: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """att_masks fp32 (B, n_objs, S, S), active int32 (B,) -> (mask_q int32 [B, S*S], mask_k int32 [B, S*S + 4*n_objs +
+    tail]) for ops.attention(mask=...)."""
+    lib = _lib.load()
+    _req(att_masks, torch.float32, "att_masks")
+    _req(active, torch.int32, "active")
+    B, K, S, S2 = att_masks.shape
+    att_masks = att_masks.contiguous()
+    P = S * S2
+    mq = torch.empty((B, P), dtype=torch.int32, device=att_masks.device)
+    mk = torch.empty((B, P + 4 * K + tail), dtype=torch.int32, device=att_masks.device)
+    check(lib.idiff_attmask_words(att_masks.data_ptr(), active.data_ptr(), mq.data_ptr(), mk.data_ptr(), B, K, P, tail,
+                                  _stream()), "idiff_attmask_words")
+    return mq, mk

@@ -233,6 +233,26 @@ def gen_extra(ref, which):
         torch.save(out_s, path_s)
 
 
+def gen_masked(ref):
+    """tests/golden/masked.pt: the reference's GatedSelfAttentionDense(efficient_attention=False) with the
+    instance-isolation mask built from `att_masks` (attention.py:187-255)."""
+    from instancediffusion_b200.weights import load_synthetic
+    out = {}
+    for name, spec in cases.MASKED_CASES.items():
+        x, objs, boxes, counts, att = cases.masked_case_inputs(name, spec)
+        mod = ref.attention.GatedSelfAttentionDense(*spec["args"], efficient_attention=False)
+        load_synthetic(mod, cases.WEIGHT_SEED, prefix=name + ".")
+        mod.eval()
+        t = time.time()
+        with torch.no_grad():
+            y = mod(x, objs, grounding_input={"att_masks": att}, drop_box_mask=False)
+            y_free = mod(x, objs)  # same block without a mask: the two must differ, or the case is vacuous
+        print(f"  {name}: {time.time() - t:.1f}s masked-vs-free rel diff {((y - y_free).norm() / y_free.norm()).item():.3e}")
+        out[name] = y[:, ::spec["stride"]].float().contiguous()
+        out[name + "/free"] = y_free[:, ::spec["stride"]].float().contiguous()
+    torch.save(out, os.path.join(GOLDEN, "masked.pt"))
+
+
 def gen_vae(ref):
     """First-stage model (tests/golden/vae.pt): the reference's AutoencoderKL (configs/test_*.yaml:42-61) with
     the synthetic weights, decode of a seeded 32x32 latent (256^2 image) and the encoder moments of a 64^2 image."""
@@ -280,6 +300,8 @@ def main():
         print("convnext cases"); gen_convnext(ref)
     if "unifusion_mask" in only:
         print("unifusion mask cases"); gen_unifusion_mask(ref)
+    if "masked" in only:
+        print("masked gated self-attention cases"); gen_masked(ref)
     if "vae" in only:
         print("first-stage (VAE) cases"); gen_vae(ref)
     if any(o.startswith("unet_extra") or o.startswith("samplers_extra") for o in only):

@@ -40,24 +40,48 @@ def feed_forward(sd: SD, p: str, x):
 FUSED_SDPA = False
 
 
-def _sdpa(q, k, v, heads):
-    """attention.py:130-144 / 183-185,257-267: head split, softmax(q k^T d^-1/2) v, head merge."""
+def _sdpa(q, k, v, heads, att_mask=None):
+    """attention.py:130-144 / 183-185,257-267: head split, softmax(q k^T d^-1/2) v, head merge.  att_mask
+    (B,1,N,N): entries <= 0 are filled with -inf before the softmax (:276-277, the non-efficient path)."""
     B, N, C = q.shape
     M = k.shape[1]
     d = C // heads
     q = q.view(B, N, heads, d).permute(0, 2, 1, 3)
     k = k.view(B, M, heads, d).permute(0, 2, 1, 3)
     v = v.view(B, M, heads, d).permute(0, 2, 1, 3)
+    if att_mask is not None:
+        sim = (q @ k.transpose(-1, -2)) * (d ** -0.5)
+        sim = sim.masked_fill(att_mask <= 0.0, float("-inf"))
+        return (torch.softmax(sim, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B, N, C)
     if FUSED_SDPA:  # what attention.py:139-143,262-266 calls; on a GPU under autocast this is the flash kernel
         return F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B, N, C)
     att = torch.softmax((q @ k.transpose(-1, -2)) * (d ** -0.5), dim=-1)
     return (att @ v).permute(0, 2, 1, 3).reshape(B, N, C)
 
 
-def self_attention(sd: SD, p: str, x, heads=HEADS):
-    """SelfAttention.forward, attention.py:174-282 (efficient path, no mask)."""
-    o = _sdpa(linear(sd, p + ".to_q", x), linear(sd, p + ".to_k", x), linear(sd, p + ".to_v", x), heads)
+def self_attention(sd: SD, p: str, x, heads=HEADS, att_mask=None):
+    """SelfAttention.forward, attention.py:174-282 (att_mask: the instance-isolation mask of :187-255)."""
+    o = _sdpa(linear(sd, p + ".to_q", x), linear(sd, p + ".to_k", x), linear(sd, p + ".to_v", x), heads, att_mask)
     return linear(sd, p + ".to_out.0", o)
+
+
+def instance_attention_mask(att_masks, N: int):
+    """attention.py:203-251 restated.  att_masks (B, n_objs, s, s) binary -> (B, 1, N, N) with N = s*s + 4*n_objs + 64:
+    two visual tokens see each other iff some instance covers both; box / mask object tokens see (and are seen by)
+    the pixels of their instance, point / scribble tokens and the trailing 64 tokens everything; 1e-9 on the
+    diagonal keeps every row alive."""
+    B, n, s1, s2 = att_masks.shape
+    wh = s1 * s2
+    m = att_masks.reshape(B, n, wh).float()
+    both = torch.einsum("bki,bkj->bij", m, m)                 # number of instances covering both pixels
+    out = torch.ones((B, 1, N, N), dtype=att_masks.dtype)
+    out[:, 0, :wh, :wh] = (both >= 1.0).to(att_masks.dtype)
+    rep = m.repeat(1, 4, 1)                                    # [box | point | scribble | mask] token rows
+    out[:, 0, wh:N - 64, :wh] = rep
+    out[:, 0, wh + n:wh + 3 * n, :wh] = 1
+    out[:, 0, :wh, wh:N - 64] = rep.transpose(1, 2)
+    out[:, 0, :wh, wh + n:wh + 3 * n] = 1
+    return out + torch.eye(N, dtype=att_masks.dtype).view(1, 1, N, N) * 1e-9
 
 
 def cross_attention(sd: SD, p: str, x, ctx, heads=HEADS):
@@ -70,12 +94,18 @@ def layer_norm(sd: SD, p: str, x):
     return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
 
 
-def gated_self_attention(sd: SD, p: str, x, objs, scale=1.0, heads=HEADS):
+def gated_self_attention(sd: SD, p: str, x, objs, scale=1.0, heads=HEADS, att_masks=None, drop_box_mask=False):
     """GatedSelfAttentionDense.forward, attention.py:304-311 -- as written there: concatenate, norm,
-    attend over all N+184 rows, keep the first N."""
+    attend over all N+184 rows, keep the first N.  att_masks (B, n_objs, 64, 64): the efficient_attention=False
+    path with the instance-isolation mask (:190-201: only at 64x64, only if some mask is set and boxes are kept)."""
     n_vis = x.shape[1]
     o = linear(sd, p + ".linear", objs)
-    a = self_attention(sd, p + ".attn", layer_norm(sd, p + ".norm1", torch.cat([x, o], dim=1)), heads)
+    att_mask = None
+    if att_masks is not None:
+        N = n_vis + o.shape[1]
+        if N - att_masks.shape[1] * 4 - 64 == 64 * 64 and float(att_masks.sum()) > 0.0 and not drop_box_mask:
+            att_mask = instance_attention_mask(att_masks, N)
+    a = self_attention(sd, p + ".attn", layer_norm(sd, p + ".norm1", torch.cat([x, o], dim=1)), heads, att_mask)
     x = x + scale * torch.tanh(sd[p + ".alpha_attn"]) * a[:, :n_vis]
     x = x + scale * torch.tanh(sd[p + ".alpha_dense"]) * feed_forward(sd, p + ".ff", layer_norm(sd, p + ".norm2", x))
     return x

@@ -101,6 +101,41 @@ SAMPLER_EXTRA_CASES = {
 }
 
 
+# instance-isolation attention mask (attention.py:187-255, efficient_attention=False, eval_local.py --use_masked_att):
+# one gated self-attention block at the 64x64 level, att_masks rasterised from seeded boxes the way
+# utils/input.py:34-37 does.  The fixture keeps every `stride`-th token row (the full output is 10 MB).
+MASKED_CASES = {
+    "gated_sa_masked": dict(args=(320, 768, 8, 40), batch=2, n=(3, 5), seed=51, stride=8),
+}
+
+
+def attmask_from_boxes(boxes, n, size=64, max_objs=30):
+    """utils/input.py:34-37,79 restated in numpy: att_masks[k][x1:x2, y1:y2] = 1 with np.round (x on the first axis)."""
+    import numpy as np
+    att = np.zeros((max_objs, size, size), dtype=np.float32)
+    for k in range(n):
+        box = [float(v) for v in boxes[k]]
+        x1, y1, x2, y2 = (int(np.round(box[0] * size)), int(np.round(box[1] * size)), int(np.round(box[2] * size)),
+                          int(np.round(box[3] * size)))
+        att[k][x1:x2, y1:y2] = 1
+    return torch.from_numpy(att)
+
+
+def masked_case_inputs(name: str, spec: dict):
+    """x (B, 4096, 320), objs (B, 184, 768), boxes (B, 30, 4), counts, att_masks (B, 30, 64, 64)."""
+    from instancediffusion_b200 import synthetic
+    B = spec["batch"]
+    x = synth_input(name, "x", (B, 64 * 64, spec["args"][0]))
+    objs = synth_input(name, "objs", (B, 184, spec["args"][1]))
+    boxes = torch.zeros((B, 30, 4))
+    att = torch.zeros((B, 30, 64, 64))
+    for b in range(B):
+        lay = synthetic.make_layout(spec["n"][b], spec["seed"] + b, "box")
+        boxes[b, :spec["n"][b]] = lay["boxes"]
+        att[b] = attmask_from_boxes(lay["boxes"], spec["n"][b])
+    return x, objs, boxes, torch.tensor(spec["n"], dtype=torch.int32), att
+
+
 # first-stage model (ldm/models/autoencoder.py): latent std 0.9 is what a finished sampler run hands to decode
 VAE_CASES = {
     "decode_32": dict(kind="decode", batch=1, size=32, seed=41, std=0.9),

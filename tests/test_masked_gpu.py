@@ -1,0 +1,156 @@
+"""`-m gpu` parity of the instance-isolation attention mask (attention.py:187-255, live with
+`efficient_attention: False` / eval_local.py --use_masked_att) and of its host prep on the GPU (section 8f-3:
+utils/input.py:34-37 box rasterisation): mask words, masked flash attention, the gated block against the reference's
+own output (tests/golden/masked.pt) and through the whole UNet (cond masked + null branch in one batched forward)."""
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(HERE, "golden")
+
+
+def _load(name):
+    path = os.path.join(GOLDEN, name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} not generated")
+    return torch.load(path, map_location="cpu")
+
+
+def test_boxes_to_attmask_matches_host_rasterisation(cuda_device):
+    """idiff_boxes_to_attmask == utils/input.py:34-37 (np.round, x on the first axis), incl. half-way coordinates."""
+    from instancediffusion_b200 import ops, synthetic
+    B = 3
+    boxes = torch.zeros((B, 30, 4))
+    counts = torch.tensor([4, 1, 0], dtype=torch.int32)
+    ref = torch.zeros((B, 30, 64, 64))
+    for b in range(B):
+        n = int(counts[b])
+        if n:
+            lay = synthetic.make_layout(n, 90 + b, "box")
+            bx = lay["boxes"].clone()
+            if b == 0:
+                bx[0] = torch.tensor([0.1171875, 0.2578125, 0.5234375, 0.7734375])  # k + 0.5 after * 64: round half even
+            boxes[b, :n] = bx
+            ref[b] = cases.attmask_from_boxes(bx, n)
+    got = ops.boxes_to_attmask(boxes.to(cuda_device), counts.to(cuda_device)).cpu()
+    assert torch.equal(got, ref)
+
+
+def test_attmask_words_match_restated_mask(cuda_device):
+    """The bit words reproduce the (B,1,N,N) mask of attention.py:203-251 on the rows the gated block keeps."""
+    from oracle import torch_oracle as TO
+    from instancediffusion_b200 import ops
+    name, spec = next(iter(cases.MASKED_CASES.items()))
+    _, _, _, _, att = cases.masked_case_inputs(name, spec)
+    B = att.shape[0]
+    N = 64 * 64 + 184
+    full = TO.instance_attention_mask(att, N)[:, 0, :64 * 64, :] > 0  # visual query rows x all keys
+    mq, mk = ops.attmask_words(att.to(cuda_device), torch.ones(B, dtype=torch.int32, device=cuda_device), tail=64)
+    mq, mk = mq.cpu(), mk.cpu()
+    for b in range(B):
+        allowed = (mq[b][:, None] & mk[b][None, :]) != 0
+        idx = torch.arange(64 * 64)
+        allowed[idx, idx] = True
+        assert torch.equal(allowed, full[b]), f"batch {b}: {(allowed != full[b]).sum().item()} mask entries differ"
+    # inactive entries: all-ones words
+    mq0, mk0 = ops.attmask_words(att.to(cuda_device), torch.zeros(B, dtype=torch.int32, device=cuda_device), tail=64)
+    assert bool((mq0 == -1).all()) and bool((mk0 == -1).all())
+
+
+def test_masked_flash_attention_vs_torch(cuda_device):
+    """attention2 (d=40) with mask words against torch softmax with the same boolean mask, two key segments."""
+    from instancediffusion_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    B, H, d, N, n1 = 2, 8, 40, 4096, 184
+    C = H * d
+    qkv = (torch.randn((B * N, 3 * C), generator=g)).to(cuda_device).half()
+    okv = (torch.randn((B * n1, 2 * C), generator=g)).to(cuda_device).half()
+    mq = torch.randint(0, 2 ** 20, (B, N), generator=g, dtype=torch.int64)
+    mq = (mq & torch.randint(0, 2 ** 20, (B, N), generator=g, dtype=torch.int64) & 0x3F).to(torch.int32)  # sparse bits
+    mk = torch.cat([mq, torch.randint(0, 64, (B, n1), generator=g, dtype=torch.int64).to(torch.int32)], 1)
+    mqd, mkd = mq.to(cuda_device).contiguous(), mk.to(cuda_device).contiguous()
+    out = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], batch=B, heads=H, head_dim=d, nq=N, n0=N,
+                        scale=d ** -0.5, k1=okv[:, :C], v1=okv[:, C:], n1=n1, kv1_batch=B, mask=(mqd, mkd)).float()
+    q = qkv[:, :C].float().view(B, N, H, d).permute(0, 2, 1, 3)
+    k = torch.cat([qkv[:, C:2 * C].float().view(B, N, C), okv[:, :C].float().view(B, n1, C)], 1).view(B, N + n1, H, d).permute(0, 2, 1, 3)
+    v = torch.cat([qkv[:, 2 * C:].float().view(B, N, C), okv[:, C:].float().view(B, n1, C)], 1).view(B, N + n1, H, d).permute(0, 2, 1, 3)
+    allowed = (mqd[:, :, None] & mkd[:, None, :]) != 0
+    idx = torch.arange(N, device=cuda_device)
+    allowed[:, idx, idx] = True
+    ref = torch.empty((B, H, N, d), device=cuda_device)
+    for b in range(B):
+        s = (q[b] @ k[b].transpose(-1, -2)) * d ** -0.5
+        s = s.masked_fill(~allowed[b][None], float("-inf"))
+        ref[b] = torch.softmax(s, -1) @ v[b]
+    ref = ref.permute(0, 2, 1, 3).reshape(B * N, C)
+    err = (out - ref).abs().max().item()
+    assert torch.isfinite(out).all() and err < 4e-3 * ref.abs().max().item() + 2e-3, err
+
+
+@pytest.mark.parametrize("name", list(cases.MASKED_CASES))
+def test_masked_gated_block_matches_reference_golden(cuda_device, name):
+    from instancediffusion_b200 import ops
+    from instancediffusion_b200.ldm.modules.attention import GatedSelfAttentionDense
+    from instancediffusion_b200.weights import load_synthetic
+    gold = _load("masked.pt")
+    spec = cases.MASKED_CASES[name]
+    x, objs, boxes, counts, att = cases.masked_case_inputs(name, spec)
+    mod = GatedSelfAttentionDense(*spec["args"], efficient_attention=False)
+    load_synthetic(mod, cases.WEIGHT_SEED, prefix=name + ".")
+    mod = mod.to(cuda_device).eval()
+    # att_masks rasterised on the GPU from the boxes (host prep, section 8f-3)
+    att_dev = ops.boxes_to_attmask(boxes.to(cuda_device), counts.to(cuda_device))
+    assert torch.equal(att_dev.cpu(), att)
+    with torch.no_grad():
+        y = mod(x.to(cuda_device), objs.to(cuda_device), grounding_input={"att_masks": att_dev}, drop_box_mask=False)
+        y_free = mod(x.to(cuda_device), objs.to(cuda_device))
+        y_drop = mod(x.to(cuda_device), objs.to(cuda_device), grounding_input={"att_masks": att_dev}, drop_box_mask=True)
+    for got, key in ((y, name), (y_free, name + "/free"), (y_drop, name + "/free")):
+        got = got[:, ::spec["stride"]].float().cpu()
+        rel = ((got - gold[key]).norm() / gold[key].norm()).item()
+        print(f"[{key}] rel_l2={rel:.3e}")
+        assert torch.isfinite(got).all() and rel < 3e-3, (key, rel)
+
+
+def test_unet_with_attention_mask_batched_equals_single(cuda_device):
+    """Whole UNet built with efficient_attention=False: the cond forward (masked fusers at the 64x64 level) and the
+    null forward batched into one call equal the two single calls, and the mask changes eps."""
+    from instancediffusion_b200 import ops, synthetic
+    from instancediffusion_b200.utils.model import set_alpha_scale
+    from instancediffusion_b200.weights import synth_tensor, unet_config
+    from instancediffusion_b200.ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from instancediffusion_b200.grounding_input.text_grounding_tokinzer_input import GroundingNetInput
+    cfg = unet_config("box")
+    cfg["efficient_attention"] = False
+    with torch.device("meta"):
+        model = UNetModel(**cfg)
+    model = model.to_empty(device=cuda_device).eval()
+    model.load_state_dict({k: synth_tensor(k, tuple(v.shape), 0) for k, v in model.state_dict().items()}, strict=True)
+    model.grounding_tokenizer_input = gti = GroundingNetInput()
+    gb = synthetic.make_grounding_batch(1, 3, 61, "box", device=cuda_device)
+    counts = torch.tensor([3], dtype=torch.int32, device=cuda_device)
+    gb["att_masks"] = ops.boxes_to_attmask(gb["boxes"], counts)
+    gi = gti.prepare(gb, return_att_masks=True)
+    x = synthetic.make_noise(1, 61, device=cuda_device)
+    ctx = synthetic.make_context(1, 62, cuda_device)
+    uc = synthetic.make_context(1, 63, cuda_device)
+    ts = torch.full((1,), 601, dtype=torch.long, device=cuda_device)
+    set_alpha_scale(model, 1)
+    cond = dict(x=x, timesteps=ts, context=ctx, grounding_input=gi)
+    null = dict(x=x, timesteps=ts, context=uc)
+    e_c, e_u = model.forward_batched([cond, null])
+    e_c1 = model(cond)
+    e_u1 = model(null)
+    gi_free = {k: v for k, v in gi.items() if k != "att_masks"}
+    e_free = model(dict(x=x, timesteps=ts, context=ctx, grounding_input=gi_free))
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    assert torch.isfinite(e_c).all() and torch.isfinite(e_u).all()
+    assert rel(e_c, e_c1) < 4e-3 and rel(e_u, e_u1) < 4e-3, (rel(e_c, e_c1), rel(e_u, e_u1))
+    assert rel(e_c1, e_free) > 5e-3, "the attention mask did not change the prediction"

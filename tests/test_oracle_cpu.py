@@ -256,3 +256,22 @@ def test_vae_restatement_matches_reference(name):
             x = torch.randn((spec["batch"], 3, spec["size"], spec["size"]), generator=g) * spec["std"]
             got = TO.vae_encode_moments(sd, x)
     _close(got, gold[name], 1e-4, 5e-5, f"vae {name}")
+
+
+# ------------------------------------------------------------------------------------------------
+# instance-isolation attention mask (efficient_attention=False path of the gated self-attention)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.MASKED_CASES))
+def test_masked_gated_attention_restatement_matches_reference(name):
+    gold = _load("masked.pt")
+    spec = cases.MASKED_CASES[name]
+    x, objs, boxes, counts, att = cases.masked_case_inputs(name, spec)
+    from instancediffusion_b200.ldm.modules.attention import GatedSelfAttentionDense
+    with torch.device("meta"):
+        m = GatedSelfAttentionDense(*spec["args"], efficient_attention=False)
+    sd = {"m." + k: synth_tensor(f"{name}.{k}", tuple(v.shape), cases.WEIGHT_SEED) for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        got = TO.gated_self_attention(sd, "m", x, objs, att_masks=att)
+        free = TO.gated_self_attention(sd, "m", x, objs)
+    _close(got[:, ::spec["stride"]], gold[name], 1e-4, 2e-5, name)
+    _close(free[:, ::spec["stride"]], gold[name + "/free"], 1e-4, 2e-5, name + "/free")
