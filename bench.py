@@ -327,7 +327,9 @@ def roofline_pass(model, device, peaks):
             f[i] += a[i]
     traffic_tab = {}
     try:
-        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        # DRAM bytes per launch per kernel family: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over one
+        # eager forward of this workload (tools/r2_profiles.sh -> tools/ncu_traffic.py)
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
     except Exception:
         pass
     dom = max(fam.items(), key=lambda kv: kv[1][0])

@@ -16,7 +16,7 @@
 namespace idiff {
 
 constexpr int GN_MAX_GROUPS = 32;
-constexpr int GN_MAX_CHUNKS = 64;
+constexpr int GN_MAX_CHUNKS = 64;  // pixel chunks per sample (two per lane in the apply pass's statistics reduction)
 
 IDIFF_DEVICE void unpack8(const uint4& v, float (&f)[8]) {
   const uint32_t u[4] = {v.x, v.y, v.z, v.w};
@@ -28,7 +28,10 @@ IDIFF_DEVICE void unpack8(const uint4& v, float (&f)[8]) {
   }
 }
 
-// grid (chunks, B), block k*CV.  partial: [B][chunks][groups][2] (sum, sumsq)
+// grid (chunks, B), block k*CV.  partial: [B][groups][GN_MAX_CHUNKS] (sum, sumsq) pairs, chunk fastest, so that the
+// apply pass reduces a group's chunks with coalesced loads and a butterfly.  (Measured, round 2: 512-thread CTAs with
+// eight loads in flight per thread and half as many chunks were SLOWER -- 4096x320: 42 vs 38 us for the pair -- the
+// pass is bound by CTA count / tail, not by loads in flight; profiles/r2_ncu_gn_stats_kernel.summary.csv.)
 __global__ void __launch_bounds__(512)
 gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int hw, int C, int groups,
                 int pix_per_block, int k) {
@@ -46,12 +49,12 @@ gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int hw
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
   int pix = p0 + r;
-  for (; pix + 3 * k < p1; pix += 4 * k) {
-    uint4 v[4];
+  for (; pix + 7 * k < p1; pix += 8 * k) {
+    uint4 v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = xb[(long)(pix + u * k) * CV];
+    for (int u = 0; u < 8; ++u) v[u] = xb[(long)(pix + u * k) * CV];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       float f[8];
       unpack8(v[u], f);
 #pragma unroll
@@ -90,7 +93,7 @@ gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int hw
           a += red[(rr * C + c) * 2];
           q += red[(rr * C + c) * 2 + 1];
         }
-        float* dst = partial + (((long)b * gridDim.x + blockIdx.x) * groups + g) * 2;
+        float* dst = partial + (((long)b * groups + g) * GN_MAX_CHUNKS + blockIdx.x) * 2;
         dst[0] = a;
         dst[1] = q;
       }
@@ -111,7 +114,7 @@ gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int hw
       q += __shfl_xor_sync(0xffffffffu, q, o);
     }
     if (lane == 0) {
-      float* dst = partial + (((long)b * gridDim.x + blockIdx.x) * groups + g) * 2;
+      float* dst = partial + (((long)b * groups + g) * GN_MAX_CHUNKS + blockIdx.x) * 2;
       dst[0] = a;
       dst[1] = q;
     }
@@ -129,18 +132,45 @@ gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float*
   const int CV = C >> 3;
   const int b = blockIdx.y;
   const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {  // blockDim may be < groups on tiny maps
-    float a = 0.f, q = 0.f;
-    for (int ch = 0; ch < stat_chunks; ++ch) {
-      const float* src = partial + (((long)b * stat_chunks + ch) * groups + g) * 2;
-      a += src[0];
-      q += src[1];
-    }
+  // statistics: one warp per group, lane = pixel chunk (one coalesced load, fixed-order butterfly) -- the round-1
+  // prologue walked up to 64 chunks serially in every CTA before the first pixel moved
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nfull = blockDim.x >> 5;
     const float inv_n = 1.0f / (float)((long)cpg * hw);
-    const float mean = a * inv_n;
-    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-    s_mean[g] = mean;
-    s_rstd[g] = rsqrtf(var + eps);
+    if (nfull == 0) {  // fewer than 32 threads (tiny maps through the C ABI): serial, same order
+      if (threadIdx.x == 0)
+        for (int g = 0; g < groups; ++g) {
+          float a = 0.f, q = 0.f;
+          for (int ch = 0; ch < stat_chunks; ++ch) {
+            const float2 v = *reinterpret_cast<const float2*>(partial + (((long)b * groups + g) * GN_MAX_CHUNKS + ch) * 2);
+            a += v.x;
+            q += v.y;
+          }
+          const float mean = a * inv_n;
+          s_mean[g] = mean;
+          s_rstd[g] = rsqrtf(fmaxf(q * inv_n - mean * mean, 0.f) + eps);
+        }
+    } else if (warp < nfull) {
+      for (int g = warp; g < groups; g += nfull) {
+        float2 v = make_float2(0.f, 0.f);
+        if (lane < stat_chunks) v = *reinterpret_cast<const float2*>(partial + (((long)b * groups + g) * GN_MAX_CHUNKS + lane) * 2);
+        if (lane + 32 < stat_chunks) {
+          const float2 w = *reinterpret_cast<const float2*>(partial + (((long)b * groups + g) * GN_MAX_CHUNKS + lane + 32) * 2);
+          v.x += w.x;
+          v.y += w.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+          v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+        }
+        if (lane == 0) {
+          const float mean = v.x * inv_n;
+          s_mean[g] = mean;
+          s_rstd[g] = rsqrtf(fmaxf(v.y * inv_n - mean * mean, 0.f) + eps);
+        }
+      }
+    }
   }
   __syncthreads();
   const int r = threadIdx.x / CV;
@@ -174,12 +204,12 @@ gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float*
     y[idx] = make_uint4(o[0], o[1], o[2], o[3]);
   };
   int pix = p0 + r;
-  for (; pix + 3 * k < p1; pix += 4 * k) {
-    uint4 v[4];
+  for (; pix + 7 * k < p1; pix += 8 * k) {
+    uint4 v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = x[base + (long)(pix + u * k) * CV];
+    for (int u = 0; u < 8; ++u) v[u] = x[base + (long)(pix + u * k) * CV];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) norm_store(v[u], base + (long)(pix + u * k) * CV);
+    for (int u = 0; u < 8; ++u) norm_store(v[u], base + (long)(pix + u * k) * CV);
   }
   for (; pix < p1; pix += k) norm_store(x[base + (long)pix * CV], base + (long)pix * CV);
 }

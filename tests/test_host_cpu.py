@@ -299,3 +299,61 @@ def test_broadcast_and_sharding_world2():
     assert res[0][2] == (16 * 32 + 32 * 8) * 2 + (32 + 32 + 32 + 8 + 5) * 4
     assert res[0][3] == [0, 2, 4, 6] and res[1][3] == [1, 3, 5]
     assert res[0][4] == 2.0 and res[1][4] == 2.0
+
+
+# ------------------------------------------------------------------------------------------------
+# request front end, checkpoint pre-pack
+# ------------------------------------------------------------------------------------------------
+def test_demo_json_front_end():
+    """inference.py:188-281 restated: xywh pixel boxes -> xyxy in [0,1], centre points, zero polygons / scribbles when
+    the request carries none (the reference discards masks, :249), per-instance metas for the Multi-instance Sampler."""
+    from instancediffusion_b200 import frontend
+    req = {"caption": "a cat and a dog", "width": 512, "height": 256,
+           "annos": [{"bbox": [0, 51, 179, 128], "mask": [], "caption": "a cat"},
+                     {"bbox": [256, 64, 128, 64], "mask": [], "caption": "a dog"}]}
+    meta, = frontend.read_request(req, alpha=0.8, mis=0.36)
+    assert meta["prompt"] == "a cat and a dog" and meta["phrases"] == ["a cat", "a dog"]
+    assert meta["locations"][0] == [0.0, 51 / 256, 179 / 512, 179 / 256]
+    assert meta["locations"][1] == [0.5, 0.25, 0.75, 0.5]
+    assert meta["points"][1] == [0.625, 0.375]
+    assert meta["alpha_type"][0] == 0.8 and abs(sum(meta["alpha_type"]) - 1) < 1e-12
+    assert len(meta["polygons"][0]) == 512 and not any(meta["polygons"][0])
+    assert len(meta["scribbles"][0]) == 40 and not any(meta["scribbles"][0])
+    assert len(meta["instance_meta"]) == 2
+    im = meta["instance_meta"][1]
+    assert im["locations"] == [meta["locations"][1]] and im["phrases"] == ["a dog"] and im["prompt"] == "a dog"
+    # explicit points / scribbles are rescaled; scribbles go through the reference's reorder / resample step
+    req["annos"][0]["point"] = [128, 64]
+    req["annos"][1]["point"] = [256, 128]
+    req["annos"][0]["scribble"] = [[i * 8, i * 4] for i in range(30)]
+    req["annos"][1]["scribble"] = [[400 - i, 200 - i] for i in range(30)]
+    meta, = frontend.read_request(req, mis=0.0)
+    assert meta["points"] == [[0.25, 0.25], [0.5, 0.5]] and "instance_meta" not in meta
+    assert all(len(s) == 40 for s in meta["scribbles"]) or len(meta["scribbles"]) == 20  # (reference quirk kept: see frontend.py)
+    ref_demo = os.path.join(os.environ.get("IDIFF_REF", "/root/reference"), "demos", "demo_cat_dog_robin.json")
+    if os.path.exists(ref_demo):
+        m, = frontend.read_request(ref_demo)
+        assert len(m["locations"]) == 4 and len(m["instance_meta"]) == 4
+        assert all(0.0 <= v <= 1.0 for box in m["locations"] for v in box)
+
+
+def test_checkpoint_prepack_roundtrip():
+    """pack -> unpack restores vectors exactly and matrices to fp16 precision; the pack is half the fp32 size."""
+    from instancediffusion_b200.utils import checkpoint as ck
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3), torch.nn.GroupNorm(2, 8), torch.nn.Linear(8, 5))
+    sd = m.state_dict()
+    pack = ck.pack_state_dict(sd)
+    n16 = sum(v.numel() for v in sd.values() if v.dim() >= 2)
+    n32 = sum(v.numel() for v in sd.values() if v.dim() < 2)
+    assert ck.pack_bytes(pack) == 2 * n16 + 4 * n32
+    m2 = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3), torch.nn.GroupNorm(2, 8), torch.nn.Linear(8, 5))
+    ck.unpack_into(m2, pack, strict=True)
+    for (k, a), (_, b) in zip(sd.items(), m2.state_dict().items()):
+        if a.dim() >= 2:
+            assert torch.equal(b, a.half().float()), k
+        else:
+            assert torch.equal(b, a), k
+    e = ck.empty_like_pack(m2, "cpu")
+    assert [i[:2] for i in e["index"]] == [i[:2] for i in pack["index"]]
+    assert e["f16"].numel() == pack["f16"].numel() and e["f32"].numel() == pack["f32"].numel()

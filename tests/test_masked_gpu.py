@@ -154,3 +154,29 @@ def test_unet_with_attention_mask_batched_equals_single(cuda_device):
     assert torch.isfinite(e_c).all() and torch.isfinite(e_u).all()
     assert rel(e_c, e_c1) < 4e-3 and rel(e_u, e_u1) < 4e-3, (rel(e_c, e_c1), rel(e_u, e_u1))
     assert rel(e_c1, e_free) > 5e-3, "the attention mask did not change the prediction"
+
+
+def test_prepare_batch_on_device(cuda_device):
+    """utils/input.py:41-125 layout built on the device: shapes, padding to 30 slots, per-instance metas with the
+    instance in slot 0, att_masks identical to the host rasterisation, zero segs as a stride-0 view."""
+    from instancediffusion_b200 import frontend
+    from instancediffusion_b200.utils.input import prepare_batch
+    req = {"caption": "x", "width": 512, "height": 512,
+           "annos": [{"bbox": [0, 51, 179, 230], "caption": "a"}, {"bbox": [300, 100, 120, 250], "caption": "b"},
+                     {"bbox": [40, 300, 200, 150], "caption": "c"}]}
+    meta, = frontend.read_request(req)
+    feats = [torch.full((768,), float(i + 1)) for i in range(3)]
+    out = prepare_batch(meta, batch=2, use_masked_att=True, device=cuda_device, text_features=feats)
+    assert out["boxes"].shape == (2, 30, 4) and out["segs"].shape == (2, 30, 512, 512) and out["segs"].stride(-1) == 0
+    assert out["polygons"].shape == (2, 30, 512) and out["scribbles"].shape == (2, 30, 40) and out["points"].shape == (2, 30, 2)
+    assert out["masks"][0].tolist() == [1.0] * 3 + [0.0] * 27 and out["text_masks"][1].tolist() == [1.0] * 3 + [0.0] * 27
+    assert torch.equal(out["text_embeddings"][0, 1].cpu(), feats[1]) and float(out["text_embeddings"][0, 3:].abs().sum()) == 0
+    boxes = torch.tensor(meta["locations"], dtype=torch.float32)
+    assert torch.equal(out["boxes"][1, :3].cpu(), boxes)
+    ref = cases.attmask_from_boxes(boxes, 3)
+    assert torch.equal(out["att_masks"][0].cpu(), ref) and torch.equal(out["att_masks"][1].cpu(), ref)
+    inst = out["instance_meta"]
+    assert len(inst) == 3
+    assert torch.equal(inst[2]["boxes"][0, 0].cpu(), boxes[2]) and float(inst[2]["boxes"][0, 1:].abs().sum()) == 0
+    assert torch.equal(inst[2]["att_masks"][0, 0].cpu(), ref[2]) and float(inst[2]["att_masks"][0, 1:].abs().sum()) == 0
+    assert torch.equal(inst[1]["text_embeddings"][0, 0].cpu(), feats[1])

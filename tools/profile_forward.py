@@ -23,6 +23,9 @@ set_alpha_scale(model, alpha)
 with torch.no_grad():
     model.forward_batched([inp, un])
     torch.cuda.synchronize()
+    if len(sys.argv) > 3 and sys.argv[3] == "cold":  # include the per-sample hoisted work (UniFusion tokens, object K/V)
+        model.clear_caches()
+        model.use_cuda_graph = False
     torch.cuda.profiler.start()
     model.forward_batched([inp, un])
     torch.cuda.synchronize()
