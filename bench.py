@@ -41,8 +41,8 @@ CONFIGS = {
                      "8 instances, 50-step PLMS, Multi-instance Sampler 0.36, alpha 0.8, fp16",
             batch=4, n=8, flavor="scribble", latent=64, mis=0.36),
     4: dict(workload="config4: batch=8 768x768 (latent 96x96), mask conditioning (test_mask flags), 16 instances, "
-                     "50-step PLMS, fp16 arithmetic (BASELINE names bf16; this library computes in fp16)",
-            batch=8, n=16, flavor="mask", latent=96, mis=0.0),
+                     "50-step PLMS, bf16 storage (libidiff_b200_bf16.so), fp32 accumulation",
+            batch=8, n=16, flavor="mask", latent=96, mis=0.0, dtype="bf16"),
     5: dict(workload="config5: batch=8 per GPU (64 over 8 GPUs) 512x512, 30 box instances, 50-step PLMS, "
                      "Multi-instance Sampler 0.36 (31 trajectories), fp16",
             batch=8, n=30, flavor="box", latent=64, mis=0.36),
@@ -214,7 +214,8 @@ def build_pipeline(device, rank, world):
     torch.cuda.synchronize()
     parallel.barrier()
     t0 = time.perf_counter()
-    sent = parallel.broadcast_module_(model, src=0)  # matrices as fp16 (2.46 GB), vectors fp32
+    from instancediffusion_b200 import ops
+    sent = parallel.broadcast_module_(model, src=0, wire_dtype=ops.HALF)  # matrices in the 16-bit storage type (2.46 GB), vectors fp32
     torch.cuda.synchronize()
     parallel.barrier()
     bcast_ms = (time.perf_counter() - t0) * 1e3 if world > 1 else 0.0
@@ -327,6 +328,8 @@ def roofline_pass(model, device, peaks):
             f[i] += a[i]
     traffic_tab = {}
     try:
+        if (BATCH, LATENT) != (4, 64):  # the table was captured on forward batch 8 at 64x64 (configs 2 / 3)
+            raise KeyError("no traffic capture for this workload")
         # DRAM bytes per launch per kernel family: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over one
         # eager forward of this workload (tools/r2_profiles.sh -> tools/ncu_traffic.py)
         traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
@@ -371,6 +374,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[N-1]")
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dtype", default=None, choices=["fp16", "bf16"],
+                    help="16-bit storage type (default: the config's own -- fp16, bf16 for config 4)")
     ap.add_argument("--no-mis-leg", action="store_true", help="skip the extra mis=0.36 leg of config 2")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -380,10 +385,12 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
-    from instancediffusion_b200 import _lib, parallel
+    from instancediffusion_b200 import _lib, ops, parallel
     from instancediffusion_b200.utils.model import set_alpha_scale
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the CUDA arm has no CPU fallback (use --impl reference)")
+    dtype_name = args.dtype or cfg.get("dtype", "fp16")
+    ops.set_storage_dtype(torch.bfloat16 if dtype_name == "bf16" else torch.float16)
     _lib.load()
     rank, local_rank, world = parallel.init_distributed()
     torch.cuda.set_device(local_rank)
@@ -472,14 +479,14 @@ def main():
     line = {
         "metric": "images/sec/GPU @512^2 fp16 50-step PLMS, 8 instances", "value": value, "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype_name, "data": "synthetic",
         "config": {"workload": WORKLOAD, "mis": args.mis, "global_batch": BATCH * world, "parallelism": f"dp{world}",
                    "forwards_per_call": fpc, "forward_batch": 2 * BATCH,
                    "l2_policy": "activations per forward (>1 GB at batch 8) exceed the 126 MB L2; roofline pass "
                                 "flushes L2 (256 MB write) between iterations",
                    "cuda_graph": bool(model.use_cuda_graph), "weights": "seeded random (no checkpoint offline)",
                    "weight_broadcast_bytes": sent, "weight_broadcast_ms": bcast_ms,
-                   "weight_broadcast_wire": "fp16 matrices + fp32 vectors, one NCCL broadcast at init"},
+                   "weight_broadcast_wire": f"{dtype_name} matrices + fp32 vectors, one NCCL broadcast at init"},
         "per_gpu_images_per_s": value / world,
         "clocks": head["clocks"],
         "e2e": {"value": head["e2e"], "unit": "images/s", "h2d_bytes_per_step": head["h2d"],

@@ -28,6 +28,16 @@ extern "C" {
 const char* idiff_last_error(void);
 int idiff_version(void);
 
+/* 16-bit storage type of the loaded library.  The same sources are compiled twice: libidiff_b200.so
+ * stores activations / weights as IEEE fp16 (the reference's torch.autocast type, inference.py:94) and
+ * libidiff_b200_bf16.so (-DIDIFF_STORAGE_BF16=1) as bfloat16 (BASELINE.json configs[3]).  Every entry
+ * point below has the same name, arguments and meaning in both; wherever a comment or a name says
+ * "fp16" / "f16" it means "the 16-bit storage type of this library".  Accumulators, normalisation
+ * statistics, biases, the sampler state and all fp32 arguments are fp32 in both. */
+#define IDIFF_DTYPE_F16 0
+#define IDIFF_DTYPE_BF16 1
+int idiff_storage_dtype(void);
+
 /* ---------------------------------------------------------------------------------------------
  * idiff_gemm: out = epilogue(A . W^T) on tcgen05 tensor cores (TMA-staged 128B-swizzled tiles,
  * fp32 accumulation in TMEM).  Replaces every nn.Linear / 1x1 conv / 3x3 conv of the path:

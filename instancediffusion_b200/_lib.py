@@ -10,6 +10,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libidiff_b200.so")
+# The same sources compiled for each 16-bit storage type (include/idiff_b200.h: idiff_storage_dtype)
+LIB_PATHS = {"f16": LIB_PATH, "bf16": os.path.join(_HERE, "csrc", "libidiff_b200_bf16.so")}
+DTYPE_CODES = {"f16": 0, "bf16": 1}
 
 
 class IdiffError(RuntimeError):
@@ -53,6 +56,7 @@ _vp, _i, _f, _l = C.c_void_p, C.c_int, C.c_float, C.c_long
 SIGNATURES = {
     "idiff_last_error": (C.c_char_p, []),
     "idiff_version": (_i, []),
+    "idiff_storage_dtype": (_i, []),
     "idiff_gemm": (_i, [C.POINTER(GemmArgs), _vp]),
     "idiff_gemm_ln_slots": (_i, [C.POINTER(GemmArgs)]),
     "idiff_row_stats": (_i, [_vp, _vp, _i, _i, _vp]),
@@ -85,25 +89,41 @@ SIGNATURES = {
     "idiff_softmax_rows": (_i, [_vp, _i, _i, _l, _vp]),
 }
 
-_lib = None
+_libs = {}
+_storage = "f16"  # which build load() returns; switched by ops.set_storage_dtype
 
 
-def load() -> C.CDLL:
-    """Load the shared library (raises if it has not been built)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def set_storage(kind: str) -> None:
+    global _storage
+    if kind not in LIB_PATHS:
+        raise IdiffError(f"unknown storage type {kind!r} (have {sorted(LIB_PATHS)})")
+    _storage = kind
+
+
+def storage() -> str:
+    return _storage
+
+
+def load(kind: str | None = None) -> C.CDLL:
+    """Load the shared library of the current (or the named) storage type; raises if it has not been built."""
+    kind = kind or _storage
+    lib = _libs.get(kind)
+    if lib is not None:
+        return lib
+    path = LIB_PATHS[kind]
+    if not os.path.exists(path):
         raise IdiffError(
-            f"{LIB_PATH} not found: the sm_100a CUDA library is required (no fallback). "
+            f"{path} not found: the sm_100a CUDA library is required (no fallback). "
             "Build it with `python -m instancediffusion_b200.build` or __graft_entry__.build()."
         )
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    if lib.idiff_storage_dtype() != DTYPE_CODES[kind]:
+        raise IdiffError(f"{path} was not built for {kind} storage")
+    _libs[kind] = lib
     return lib
 
 

@@ -13,6 +13,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libidiff_b200.so")
+LIB_BF16 = os.path.join(CSRC, "libidiff_b200_bf16.so")  # same sources, -DIDIFF_STORAGE_BF16=1 (include/idiff_b200.h)
 SOURCES = ["host.cu", "gemm2.cu", "attention.cu", "attention2.cu", "norm.cu", "scaleu.cu", "elementwise.cu", "convnext.cu", "vae.cu"]
 HEADERS = ["common.cuh", "host.cuh", os.path.join("..", "..", "include", "idiff_b200.h")]
 
@@ -41,23 +42,24 @@ def _digest() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu to an object (in parallel) and link the shared library."""
+    """Compile every .cu to an object (in parallel), once per storage type, and link the two shared libraries."""
     stamp = os.path.join(CSRC, ".build_stamp")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp):
+    if not force and os.path.exists(LIB) and os.path.exists(LIB_BF16) and os.path.exists(stamp):
         with open(stamp) as fh:
             if fh.read().strip() == dig:
                 return LIB
     nvcc = _nvcc()
-    objs = []
+    objs = {LIB: [], LIB_BF16: []}
     procs = []
-    for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for lib, suffix, defs in ((LIB, ".o", []), (LIB_BF16, ".bf16.o", ["-DIDIFF_STORAGE_BF16=1"])):
+        for src in SOURCES:
+            obj = os.path.join(CSRC, src.replace(".cu", suffix))
+            objs[lib].append(obj)
+            cmd = [nvcc, *NVCC_FLAGS, *defs, "-c", os.path.join(CSRC, src), "-o", obj]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            procs.append((src + suffix, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
         out, _ = p.communicate()
@@ -68,10 +70,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(f"[build] {src}:\n{out}\n")
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    link = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
-    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("link failed:\n" + r.stdout)
+    for lib, lobjs in objs.items():
+        link = [nvcc, "-shared", "-o", lib, *lobjs, "-gencode", "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout)
     with open(stamp, "w") as fh:
         fh.write(dig)
     return LIB

@@ -32,7 +32,7 @@ constexpr int BQ = 128;
 struct AttnKParams {
   int heads, nq, n0, n1, kv1_broadcast;
   float scale_log2e;
-  __half* out;
+  h16* out;
   int out_ld;
 };
 
@@ -138,8 +138,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // uniform registers and the UMMAs of a product issue back to back (see gemm2.cu: as a single-lane loop every
     // tcgen05.mma cost ~20 instructions of R2UR moves and an ELECT retry loop on the pacing thread)
     {
-      constexpr uint32_t idesc_qk = make_idesc_f16(BQ, BKV, 0, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_f16(BQ, DV, 0, 0, /*B MN-major*/ 1);
+      constexpr uint32_t idesc_qk = make_idesc_f16(BQ, BKV, UMMA_AB_FMT, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_f16(BQ, DV, UMMA_AB_FMT, 0, /*B MN-major*/ 1);
       const uint32_t q_base = smem_u32(sQ);
       const uint32_t p_base = smem_u32(sP);
       auto issue_qk = [&](int j) {
@@ -275,7 +275,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float inv_l = 1.0f / l_run;
     const int qrow = q0 + r;
     const bool row_ok = qrow < p.nq;
-    __half* orow = p.out + ((long)b * p.nq + qrow) * p.out_ld + h * D;
+    h16* orow = p.out + ((long)b * p.nq + qrow) * p.out_ld + h * D;
 #pragma unroll
     for (int c0 = 0; c0 < DV; c0 += 32) {
       if (c0 >= D) break;
@@ -337,7 +337,7 @@ static int launch_attention(const idiff_attn_args* a, cudaStream_t stream) {
   p.n1 = a->n1;
   p.kv1_broadcast = (a->kv1_batch == 1) ? 1 : 0;
   p.scale_log2e = a->scale * 1.4426950408889634f;
-  p.out = reinterpret_cast<__half*>(a->out);
+  p.out = reinterpret_cast<h16*>(a->out);
   p.out_ld = a->out_ld;
   static bool attr_set = false;
   if (!attr_set) {

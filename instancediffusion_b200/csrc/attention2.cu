@@ -35,7 +35,7 @@ constexpr int BKV = 64;
 struct Params {
   int heads, nq, n0, n1, kv1_broadcast;
   float scale_log2e;
-  __half* out;
+  h16* out;
   int out_ld;
   // instance-isolation mask of the gated self-attention (attention.py:187-255): query i may attend key j iff
   // (mask_q[b][i] & mask_k[b][j]) != 0, or j is the visual token i itself (the reference's 1e-9 diagonal)
@@ -282,8 +282,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     // 64-key step.  Uniform, the UMMAs of a product issue back to back from uniform registers (gemm2.cu, same
     // measurement).  Stage / phase of every ring are running counters (no div / mod by 3).
     {
-      constexpr uint32_t idesc_qk = make_idesc_f16(BQ, BKV, 0, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_f16(BQ, C::DV, 0, 0, /*B MN-major*/ 1);
+      constexpr uint32_t idesc_qk = make_idesc_f16(BQ, BKV, UMMA_AB_FMT, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_f16(BQ, C::DV, UMMA_AB_FMT, 0, /*B MN-major*/ 1);
       // Every descriptor here shares its high word (SBO = 1024 B, version 1, SWIZZLE_128B); the low
       // word is (address >> 4) | (LBO >> 4) << 16, so stepping an operand by X bytes is lo += X >> 4.
       constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -507,7 +507,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const float inv_l = 1.0f / l;
     const int qrow = q0 + q * BQ + r;
     const bool row_ok = qrow < p.nq;
-    __half* orow = p.out + ((long)b * p.nq + qrow) * p.out_ld + h * D;
+    h16* orow = p.out + ((long)b * p.nq + qrow) * p.out_ld + h * D;
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 32) {
       if (c0 >= D) break;
@@ -584,7 +584,7 @@ int attention_v2_d40(const idiff_attn_args* a, cudaStream_t stream) {
   p.n1 = a->n1;
   p.kv1_broadcast = (a->kv1_batch == 1) ? 1 : 0;
   p.scale_log2e = a->scale * 1.4426950408889634f;
-  p.out = reinterpret_cast<__half*>(a->out);
+  p.out = reinterpret_cast<h16*>(a->out);
   p.out_ld = a->out_ld;
   p.mask_q = reinterpret_cast<const uint32_t*>(a->mask_q);
   p.mask_k = reinterpret_cast<const uint32_t*>(a->mask_k);

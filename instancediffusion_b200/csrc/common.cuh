@@ -4,6 +4,16 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+// 16-bit storage type of this build of the library.  The library is compiled twice from the same sources:
+// libidiff_b200.so (fp16 activations / weights, the reference's autocast type, inference.py:94) and
+// libidiff_b200_bf16.so (-DIDIFF_STORAGE_BF16=1, BASELINE config 3).  Accumulation, statistics and the
+// sampler state are fp32 in both; only the operand format of the UMMAs and the pack / unpack at the
+// edges of each kernel differ, so every kernel below is written against h16 / pack_half2 / unpack_half2.
+#ifndef IDIFF_STORAGE_BF16
+#define IDIFF_STORAGE_BF16 0
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -297,6 +307,21 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, ui
 // ----------------------------------------------------------------------------------
 // numerics
 // ----------------------------------------------------------------------------------
+#if IDIFF_STORAGE_BF16
+using h16 = __nv_bfloat16;
+constexpr uint32_t UMMA_AB_FMT = 1;  // kind::f16 operand format field: bf16
+IDIFF_DEVICE uint32_t pack_half2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+IDIFF_DEVICE float2 unpack_half2(uint32_t u) {  // bf16 is the upper half of an fp32: two integer ops
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+IDIFF_DEVICE float h2f(h16 x) { return __bfloat162float(x); }
+IDIFF_DEVICE h16 f2h(float x) { return __float2bfloat16_rn(x); }
+#else
+using h16 = __half;
+constexpr uint32_t UMMA_AB_FMT = 0;  // fp16
 IDIFF_DEVICE uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -305,6 +330,9 @@ IDIFF_DEVICE float2 unpack_half2(uint32_t u) {
   __half2 h = *reinterpret_cast<__half2*>(&u);
   return __half22float2(h);
 }
+IDIFF_DEVICE float h2f(h16 x) { return __half2float(x); }
+IDIFF_DEVICE h16 f2h(float x) { return __float2half_rn(x); }
+#endif
 IDIFF_DEVICE float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 // Exact (erf) GELU of attention.py:43, x * 0.5 * (1 + erf(x / sqrt 2)), with erf from
 // Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the fp16 output resolution): one MUFU.RCP,

@@ -23,7 +23,7 @@ namespace idiff {
 constexpr int INCONV_MAX_CI = 32;
 __global__ void __launch_bounds__(256)
 segs_inconv_kernel(const float* __restrict__ segs, const float* __restrict__ w, const float* __restrict__ bias,
-                   __half* __restrict__ y, float* __restrict__ seg_sum, int B, int CI, int S, int R,
+                   h16* __restrict__ y, float* __restrict__ seg_sum, int B, int CI, int S, int R,
                    long sb, long sc, long sy, long sx) {
   pdl_launch_dependents();
   pdl_wait();
@@ -65,10 +65,10 @@ segs_inconv_kernel(const float* __restrict__ segs, const float* __restrict__ w, 
         }
       }
     }
-    __half* o = y + (((long)b * R + oy) * R + ox) * 3;
-    o[0] = __float2half(acc0 + bias[0]);
-    o[1] = __float2half(acc1 + bias[1]);
-    o[2] = __float2half(acc2 + bias[2]);
+    h16* o = y + (((long)b * R + oy) * R + ox) * 3;
+    o[0] = f2h(acc0 + bias[0]);
+    o[1] = f2h(acc1 + bias[1]);
+    o[2] = f2h(acc2 + bias[2]);
   }
   // per-sample sum of the resized masks (block reduce, one atomic per block; masks are >= 0 in practice,
   // so the order of this fp32 sum cannot change the `> 0` test it feeds)
@@ -89,7 +89,7 @@ segs_inconv_kernel(const float* __restrict__ segs, const float* __restrict__ w, 
 // these rows.  VEC = 8 halves per thread when C % 8 == 0, scalar otherwise (the C = 3 stem).
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
-__global__ void patchify_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W, int C,
+__global__ void patchify_kernel(const h16* __restrict__ x, h16* __restrict__ y, int B, int H, int W, int C,
                                 int p) {
   pdl_launch_dependents();
   pdl_wait();
@@ -170,9 +170,9 @@ dwconv7x7_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const
 // feat: fp16 NHWC [B, P, C]; null_pos: fp16 [T, F] = null_seg + pos (precomputed); pos: fp32 [T, F];
 // seg_sum: fp32 [B]; out: fp16 [B*T, F].
 // ---------------------------------------------------------------------------------------------
-__global__ void seg_tokens_kernel(const __half* __restrict__ feat, const __half* __restrict__ null_pos,
+__global__ void seg_tokens_kernel(const h16* __restrict__ feat, const h16* __restrict__ null_pos,
                                   const float* __restrict__ pos, const float* __restrict__ seg_sum,
-                                  __half* __restrict__ out, int B, int P, int C, int T) {
+                                  h16* __restrict__ out, int B, int P, int C, int T) {
   pdl_launch_dependents();
   pdl_wait();
   const int F = C * P / T;
@@ -185,7 +185,7 @@ __global__ void seg_tokens_kernel(const __half* __restrict__ feat, const __half*
     if (seg_sum[b] > 0.f) {
       const long flat = (long)r * T + t;
       const int c = (int)(flat / P), q = (int)(flat - (long)c * P);
-      out[i] = __float2half(__half2float(feat[((long)b * P + q) * C + c]) + pos[(long)t * F + r]);
+      out[i] = f2h(h2f(feat[((long)b * P + q) * C + c]) + pos[(long)t * F + r]);
     } else {
       out[i] = null_pos[(long)t * F + r];
     }
@@ -211,7 +211,7 @@ extern "C" int idiff_segs_inconv(const float* segs, const long* strides, const f
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   IDIFF_CHECK_CUDA(cudaMemsetAsync(seg_sum, 0, sizeof(float) * batch, s));
   dim3 grid((out_size + 255) / 256, out_size, batch);
-  IDIFF_CHECK_CUDA(launch_pdl(segs_inconv_kernel, grid, dim3(256), 0, s, segs, w, bias, reinterpret_cast<__half*>(y),
+  IDIFF_CHECK_CUDA(launch_pdl(segs_inconv_kernel, grid, dim3(256), 0, s, segs, w, bias, reinterpret_cast<h16*>(y),
                               seg_sum, batch, cin, in_size, out_size, strides[0], strides[1], strides[2], strides[3]));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -222,8 +222,8 @@ extern "C" int idiff_patchify(const void* x, void* y, int batch, int h, int w, i
   IDIFF_REQUIRE(x && y, "idiff_patchify: null pointer argument");
   IDIFF_REQUIRE(p > 0 && h % p == 0 && w % p == 0, "idiff_patchify: H=%d W=%d must be multiples of p=%d", h, w, p);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const __half* xi = reinterpret_cast<const __half*>(x);
-  __half* yo = reinterpret_cast<__half*>(y);
+  const h16* xi = reinterpret_cast<const h16*>(x);
+  h16* yo = reinterpret_cast<h16*>(y);
   if (c % 8 == 0) {
     const long total = (long)batch * h * w * (c / 8);
     IDIFF_CHECK_CUDA(launch_pdl(patchify_kernel<8>, dim3(grid_for(total, 256)), dim3(256), 0, s, xi, yo, batch, h, w, c, p));
@@ -257,8 +257,8 @@ extern "C" int idiff_seg_tokens(const void* feat, const void* null_pos, const fl
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long total = (long)batch * channels * pixels;
   IDIFF_CHECK_CUDA(launch_pdl(seg_tokens_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s,
-                              reinterpret_cast<const __half*>(feat), reinterpret_cast<const __half*>(null_pos), pos,
-                              seg_sum, reinterpret_cast<__half*>(out), batch, pixels, channels, tokens));
+                              reinterpret_cast<const h16*>(feat), reinterpret_cast<const h16*>(null_pos), pos,
+                              seg_sum, reinterpret_cast<h16*>(out), batch, pixels, channels, tokens));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

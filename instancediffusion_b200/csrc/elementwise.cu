@@ -11,7 +11,7 @@ namespace idiff {
 // ---------------------------------------------------------------------------------------------
 // layout conversion
 // ---------------------------------------------------------------------------------------------
-__global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int B,
+__global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, h16* __restrict__ y, int B,
                                             int C, int HW, int CP) {
   pdl_launch_dependents();  // programmatic dependent launch: the next kernel may start its prologue
   pdl_wait();               // ... and this one touches global memory only after its predecessor finished
@@ -21,10 +21,10 @@ __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ x, __half*
     const long bp = i / CP;
     const int b = (int)(bp / HW);
     const int pix = (int)(bp - (long)b * HW);
-    y[i] = (c < C) ? __float2half(x[((long)b * C + c) * HW + pix]) : __float2half(0.f);
+    y[i] = (c < C) ? f2h(x[((long)b * C + c) * HW + pix]) : f2h(0.f);
   }
 }
-__global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ x, float* __restrict__ y, int B,
+__global__ void nhwc_f16_to_nchw_f32_kernel(const h16* __restrict__ x, float* __restrict__ y, int B,
                                             int C, int HW) {
   pdl_launch_dependents();  // programmatic dependent launch: the next kernel may start its prologue
   pdl_wait();               // ... and this one touches global memory only after its predecessor finished
@@ -34,7 +34,7 @@ __global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ x, float*
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int pix = p0 + j, c = c0 + threadIdx.x;
-    tile[j][threadIdx.x] = (pix < HW && c < C) ? __half2float(x[((long)b * HW + pix) * C + c]) : 0.f;
+    tile[j][threadIdx.x] = (pix < HW && c < C) ? h2f(x[((long)b * HW + pix) * C + c]) : 0.f;
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -93,7 +93,7 @@ __constant__ float c_freqs[16];
 __global__ void __launch_bounds__(256)
 fourier_embed_kernel(const float* __restrict__ coords, const float* __restrict__ masks,
                      const float* __restrict__ text, const float* __restrict__ null_text,
-                     const float* __restrict__ null_pos, __half* __restrict__ out, int D,
+                     const float* __restrict__ null_pos, h16* __restrict__ out, int D,
                      int text_dim, int out_ld, int mask_mode, int dropped) {
   pdl_launch_dependents();  // programmatic dependent launch: the next kernel may start its prologue
   pdl_wait();               // ... and this one touches global memory only after its predecessor finished
@@ -122,10 +122,10 @@ fourier_embed_kernel(const float* __restrict__ coords, const float* __restrict__
     __syncthreads();
     mpos = s_mpos;
   }
-  __half* orow = out + (long)row * out_ld;
+  h16* orow = out + (long)row * out_ld;
   if (text) {
     for (int j = threadIdx.x; j < text_dim; j += blockDim.x)
-      orow[j] = __float2half(text[(long)row * text_dim + j] * m + (1.f - m) * null_text[j]);
+      orow[j] = f2h(text[(long)row * text_dim + j] * m + (1.f - m) * null_text[j]);
   }
   const int E = 32 * D;
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
@@ -135,12 +135,12 @@ fourier_embed_kernel(const float* __restrict__ coords, const float* __restrict__
     const int j = is_cos ? rem - D : rem;
     const float arg = c_freqs[k] * xr[j];
     const float val = is_cos ? cosf(arg) : sinf(arg);
-    orow[text_dim + e] = __float2half(val * mpos + (1.f - mpos) * null_pos[e]);
+    orow[text_dim + e] = f2h(val * mpos + (1.f - mpos) * null_pos[e]);
   }
 }
 
 // timestep_embedding (util.py:160-180): [cos(t f) | sin(t f)], f_k = exp(-ln(1e4) k / half)
-__global__ void timestep_embedding_kernel(const float* __restrict__ t, __half* __restrict__ out, int B,
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, h16* __restrict__ out, int B,
                                           int dim) {
   pdl_launch_dependents();  // programmatic dependent launch: the next kernel may start its prologue
   pdl_wait();               // ... and this one touches global memory only after its predecessor finished
@@ -150,8 +150,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, __half* _
   const int b = i / half_dim, k = i - b * half_dim;
   const float f = expf(-9.210340371976184f * (float)k / (float)half_dim);
   const float arg = t[b] * f;
-  out[(long)b * dim + k] = __float2half(cosf(arg));
-  out[(long)b * dim + half_dim + k] = __float2half(sinf(arg));
+  out[(long)b * dim + k] = f2h(cosf(arg));
+  out[(long)b * dim + half_dim + k] = f2h(sinf(arg));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -193,11 +193,11 @@ __global__ void latent_mean_kernel(const float* const* __restrict__ xs, int coun
   }
 }
 
-__global__ void silu_f16_kernel(const __half* __restrict__ x, __half* __restrict__ y, long n) {
+__global__ void silu_f16_kernel(const h16* __restrict__ x, h16* __restrict__ y, long n) {
   pdl_launch_dependents();  // programmatic dependent launch: the next kernel may start its prologue
   pdl_wait();               // ... and this one touches global memory only after its predecessor finished
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-    y[i] = __float2half(silu_f(__half2float(x[i])));
+    y[i] = f2h(silu_f(h2f(x[i])));
 }
 
 static inline int grid_for(long total, int threads) {
@@ -272,7 +272,7 @@ extern "C" int idiff_nchw_f32_to_nhwc_f16(const float* x, void* y, int batch, in
                                           void* stream) {
   IDIFF_REQUIRE(x && y && c_pad >= c, "idiff_nchw_f32_to_nhwc_f16: bad arguments");
   const long total = (long)batch * hw * c_pad;
-  IDIFF_CHECK_CUDA(launch_pdl(nchw_f32_to_nhwc_f16_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),  x, reinterpret_cast<__half*>(y), batch, c, hw, c_pad));
+  IDIFF_CHECK_CUDA(launch_pdl(nchw_f32_to_nhwc_f16_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),  x, reinterpret_cast<h16*>(y), batch, c, hw, c_pad));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -280,7 +280,7 @@ extern "C" int idiff_nchw_f32_to_nhwc_f16(const float* x, void* y, int batch, in
 extern "C" int idiff_nhwc_f16_to_nchw_f32(const void* x, float* y, int batch, int c, int hw, void* stream) {
   IDIFF_REQUIRE(x && y, "idiff_nhwc_f16_to_nchw_f32: null pointer argument");
   dim3 grid((hw + 31) / 32, (c + 31) / 32, batch);
-  IDIFF_CHECK_CUDA(launch_pdl(nhwc_f16_to_nchw_f32_kernel, dim3(grid), dim3(dim3(32, 8)), 0, reinterpret_cast<cudaStream_t>(stream),  reinterpret_cast<const __half*>(x), y, batch, c, hw));
+  IDIFF_CHECK_CUDA(launch_pdl(nhwc_f16_to_nchw_f32_kernel, dim3(grid), dim3(dim3(32, 8)), 0, reinterpret_cast<cudaStream_t>(stream),  reinterpret_cast<const h16*>(x), y, batch, c, hw));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -322,7 +322,7 @@ extern "C" int idiff_fourier_embed(const float* coords, const float* masks, cons
     IDIFF_CHECK_CUDA(cudaMemcpyToSymbol(c_freqs, f, sizeof(f)));
     freqs_set = true;
   }
-  IDIFF_CHECK_CUDA(launch_pdl(fourier_embed_kernel, dim3(rows), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),  coords, masks, text, null_text, null_pos, reinterpret_cast<__half*>(out), coord_dim, text ? text_dim : 0, out_ld, mask_mode, dropped));
+  IDIFF_CHECK_CUDA(launch_pdl(fourier_embed_kernel, dim3(rows), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),  coords, masks, text, null_text, null_pos, reinterpret_cast<h16*>(out), coord_dim, text ? text_dim : 0, out_ld, mask_mode, dropped));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -330,7 +330,7 @@ extern "C" int idiff_fourier_embed(const float* coords, const float* masks, cons
 extern "C" int idiff_timestep_embedding(const float* t, void* out, int batch, int dim, void* stream) {
   IDIFF_REQUIRE(t && out && dim % 2 == 0, "idiff_timestep_embedding: bad arguments");
   const int total = batch * dim / 2;
-  IDIFF_CHECK_CUDA(launch_pdl(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream),  t, reinterpret_cast<__half*>(out), batch, dim));
+  IDIFF_CHECK_CUDA(launch_pdl(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream),  t, reinterpret_cast<h16*>(out), batch, dim));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -354,7 +354,7 @@ extern "C" int idiff_latent_mean(const float* const* xs_dev, int count, float* o
 
 extern "C" int idiff_silu_f16(const void* x, void* y, long n, void* stream) {
   IDIFF_REQUIRE(x && y && n > 0, "idiff_silu_f16: bad arguments");
-  IDIFF_CHECK_CUDA(launch_pdl(silu_f16_kernel, dim3(grid_for(n, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),  reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), n));
+  IDIFF_CHECK_CUDA(launch_pdl(silu_f16_kernel, dim3(grid_for(n, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),  reinterpret_cast<const h16*>(x), reinterpret_cast<h16*>(y), n));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

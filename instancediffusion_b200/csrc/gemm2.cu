@@ -55,8 +55,8 @@ struct Params {
   int conv, H, W, Bn, PW, PH, PB, tiles_w, tiles_h, kb_per_tap;
   // epilogue
   const float* bias;
-  const __half* rowadd;
-  const __half* residual;
+  const h16* rowadd;
+  const h16* residual;
   void* out;
   int ldo, ldr, ldra, rows_per_batch, flags;
   float gate;
@@ -480,7 +480,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // per UMMA; this way they live in uniform registers and the four UMMAs of a k-block issue back to back
     // (UTCHMMA x4, UTCBAR).  Descriptors = (low word + constant high word), one add per UMMA; running
     // stage / phase instead of div / mod.
-    constexpr uint32_t idesc = make_idesc_f16(BM * CG, BN, 0, 0, 0);
+    constexpr uint32_t idesc = make_idesc_f16(BM * CG, BN, UMMA_AB_FMT, 0, 0);
     constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B, version 1, SWIZZLE_128B
     const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);  // LBO (unused, swizzled K-major) = 16 B
     const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -668,7 +668,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
       if (!TMA_EPI && has_res) {
-        const __half* res_row = p.residual + out_row * p.ldr + out_col_base;
+        const h16* res_row = p.residual + out_row * p.ldr + out_col_base;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
           const int c0 = chunk_col(ch);
@@ -693,7 +693,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           float val = 0.f;
           if (col < p.N) {
             if (p.bias) val = __ldg(p.bias + col);
-            if (tab_rowadd && b0 + pb < p.Bn) val += __half2float(p.rowadd[(long)(b0 + pb) * p.ldra + col]);
+            if (tab_rowadd && b0 + pb < p.Bn) val += h2f(p.rowadd[(long)(b0 + pb) * p.ldra + col]);
           }
           tab[idx] = val;
           if (p.ln_in) tab[BN + idx] = (col < p.N) ? __ldg(p.ln_s + col) : 0.f;  // row 1: sum_k W'[col, k]
@@ -819,8 +819,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait(&res_bar[ew], res_phase);
           res_phase ^= 1;
         }
-        __half* o_row = reinterpret_cast<__half*>(p.out) + out_row * p.ldo + out_col_base;
-        const __half* radd_row = p.rowadd ? p.rowadd + (long)batch_idx * p.ldra + n0 : nullptr;
+        h16* o_row = reinterpret_cast<h16*>(p.out) + out_row * p.ldo + out_col_base;
+        const h16* radd_row = p.rowadd ? p.rowadd + (long)batch_idx * p.ldra + n0 : nullptr;
         const float gate = p.gate;
         if (TMA_EPI && !nchw) {
           // Compact rolled loop (one 16-column chunk per trip, ~150 instructions, explicit
@@ -922,7 +922,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               if (slow_rowadd && row_ok) {
 #pragma unroll
                 for (int j = 0; j < CHUNK; ++j)
-                  if (out_c + j < n_out_total) x[j] += __half2float(radd_row[c0 + j]);
+                  if (out_c + j < n_out_total) x[j] += h2f(radd_row[c0 + j]);
               }
               if (do_silu) {
 #pragma unroll
@@ -1220,8 +1220,8 @@ static int launch(const idiff_gemm_args* a, cudaStream_t stream, bool want_sk) {
   p.K = a->K;
   p.KB = (a->K + BK - 1) / BK;
   p.bias = a->bias;
-  p.rowadd = reinterpret_cast<const __half*>(a->rowadd);
-  p.residual = reinterpret_cast<const __half*>(a->residual);
+  p.rowadd = reinterpret_cast<const h16*>(a->rowadd);
+  p.residual = reinterpret_cast<const h16*>(a->residual);
   p.out = a->out;
   p.ldo = a->ldo;
   p.ldr = a->ldr;

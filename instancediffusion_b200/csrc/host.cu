@@ -65,7 +65,7 @@ int encode_tmap_f16_sw(CUtensorMap* map, const void* base, int rank, const uint6
   for (int i = 0; i + 1 < rank; ++i)
     if (gstr[i] % 16 != 0) return set_error("tensor map stride %d = %llu not a multiple of 16", i,
                                             (unsigned long long)gstr[i]);
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+  CUresult r = fn(map, IDIFF_STORAGE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                   gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -88,4 +88,5 @@ bool pdl_enabled() {
 }  // namespace idiff
 
 extern "C" const char* idiff_last_error(void) { return idiff::g_err; }
-extern "C" int idiff_version(void) { return 1; }
+extern "C" int idiff_version(void) { return 2; }
+extern "C" int idiff_storage_dtype(void) { return IDIFF_STORAGE_BF16 ? IDIFF_DTYPE_BF16 : IDIFF_DTYPE_F16; }

@@ -6,6 +6,10 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#ifndef IDIFF_STORAGE_BF16
+#define IDIFF_STORAGE_BF16 0  // see common.cuh: 16-bit storage type of this build
+#endif
+
 namespace idiff {
 
 int set_error(const char* fmt, ...);  // always returns -1

@@ -49,12 +49,12 @@ vae_latent_in_kernel(const float* __restrict__ z, const float* __restrict__ w, c
 
 // one CTA per row; the row lives in shared memory as fp32 between the passes
 __global__ void __launch_bounds__(256)
-softmax_rows_kernel(__half* __restrict__ x, int n, long ld) {
+softmax_rows_kernel(h16* __restrict__ x, int n, long ld) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float srow[];
   __shared__ float red[8];
-  __half* row = x + (long)blockIdx.x * ld;
+  h16* row = x + (long)blockIdx.x * ld;
   const int nv = n >> 3;  // n % 8 == 0
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float m = -INFINITY;
@@ -129,7 +129,7 @@ extern "C" int idiff_softmax_rows(void* x, int rows, int n, long ld, void* strea
     attr_set = true;
   }
   IDIFF_CHECK_CUDA(launch_pdl(softmax_rows_kernel, dim3(rows), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream),
-                              reinterpret_cast<__half*>(x), n, ld));
+                              reinterpret_cast<h16*>(x), n, ld));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

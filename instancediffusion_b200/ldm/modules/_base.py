@@ -7,15 +7,19 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from ... import _lib
+from ... import _lib, ops
 
-HALF = torch.float16
+
+def half() -> torch.dtype:
+    """The current 16-bit storage type (ops.set_storage_dtype)."""
+    return ops.HALF
 
 
 class PackedModule(nn.Module):
     def __init__(self):
         super().__init__()
         self._pk = None
+        self._pk_epoch = -1
 
     # -- cache invalidation -----------------------------------------------------------------
     def _apply(self, fn, *a, **k):
@@ -33,8 +37,9 @@ class PackedModule(nn.Module):
 
     # -- pack access ------------------------------------------------------------------------
     def pk(self):
-        if self._pk is None:
+        if self._pk is None or self._pk_epoch != ops.STORAGE_EPOCH:  # (a storage-type switch re-packs)
             with torch.no_grad():
+                self._pk_epoch = ops.STORAGE_EPOCH
                 self._pk = self._pack()
         return self._pk
 
@@ -60,7 +65,7 @@ def dev_of(p: torch.Tensor) -> torch.device:
 
 def w16(p: torch.Tensor) -> torch.Tensor:
     dev_of(p)
-    return p.detach().to(HALF).contiguous()
+    return p.detach().to(half()).contiguous()
 
 
 def f32(p: torch.Tensor) -> torch.Tensor:
@@ -71,14 +76,14 @@ def f32(p: torch.Tensor) -> torch.Tensor:
 def to_tokens(x: torch.Tensor):
     """(B, N, C) any float dtype -> fp16 [B*N, C] contiguous."""
     B, N, C = x.shape
-    return x.reshape(B * N, C).to(HALF).contiguous(), B, N
+    return x.reshape(B * N, C).to(half()).contiguous(), B, N
 
 
 def nchw_to_nhwc16(x: torch.Tensor):
     """(B, C, H, W) -> fp16 [B*H*W, C] (boundary glue of the module-level API; the UNet fast path
     converts once with idiff_nchw_f32_to_nhwc_f16)."""
     B, C, H, W = x.shape
-    return x.permute(0, 2, 3, 1).reshape(B * H * W, C).to(HALF).contiguous(), B, H, W
+    return x.permute(0, 2, 3, 1).reshape(B * H * W, C).to(half()).contiguous(), B, H, W
 
 
 def nhwc16_to_nchw(y: torch.Tensor, B: int, H: int, W: int, dtype) -> torch.Tensor:

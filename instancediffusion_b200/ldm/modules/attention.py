@@ -23,7 +23,7 @@ import torch.nn as nn
 
 from ... import ops
 from ...packing import pack_conv1x1, pack_geglu
-from ._base import HALF, PackedModule, f32, nchw_to_nhwc16, nhwc16_to_nchw, to_tokens, w16
+from ._base import half, PackedModule, f32, nchw_to_nhwc16, nhwc16_to_nchw, to_tokens, w16
 from .diffusionmodules.util import zero_module
 
 

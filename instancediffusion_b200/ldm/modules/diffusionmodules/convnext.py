@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from .... import ops
-from .._base import HALF, PackedModule, f32, nchw_to_nhwc16, nhwc16_to_nchw, w16
+from .._base import half, PackedModule, f32, nchw_to_nhwc16, nhwc16_to_nchw, w16
 
 
 class LayerNorm(nn.Module):
@@ -60,7 +60,7 @@ class Block(PackedModule):
             "bd": f32(self.dwconv.bias),
             "ng": f32(self.norm.weight), "nb": f32(self.norm.bias),
             "w1": w16(self.pwconv1.weight), "b1": f32(self.pwconv1.bias),
-            "w2": w2.to(HALF).contiguous(), "b2": b2.contiguous(),
+            "w2": w2.to(half()).contiguous(), "b2": b2.contiguous(),
         }
 
     def _fwd(self, x16, B, H, W):

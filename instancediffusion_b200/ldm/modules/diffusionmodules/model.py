@@ -24,7 +24,7 @@ import torch.nn as nn
 
 from .... import ops
 from ....packing import pack_conv1x1, pack_conv3x3
-from .._base import HALF, PackedModule, f32, nchw_to_nhwc16, nhwc16_to_nchw, w16
+from .._base import half, PackedModule, f32, nchw_to_nhwc16, nhwc16_to_nchw, w16
 
 
 def nonlinearity(x):
@@ -40,10 +40,10 @@ def _pad64(c: int) -> int:
 
 
 def _pack3x3(conv: nn.Conv2d, cin_pad: int | None = None) -> torch.Tensor:
-    w = conv.weight.detach().to(HALF)
+    w = conv.weight.detach().to(half())
     cout, cin = w.shape[:2]
     if cin_pad is not None and cin_pad != cin:
-        wp = torch.zeros((cout, cin_pad, 3, 3), dtype=HALF, device=w.device)
+        wp = torch.zeros((cout, cin_pad, 3, 3), dtype=half(), device=w.device)
         wp[:, :cin] = w
         w = wp
     return pack_conv3x3(w.contiguous())
@@ -174,10 +174,10 @@ class AttnBlock(PackedModule):
         bo = self.proj_out.bias.detach().float() + wo @ self.v.bias.detach().float()
         return {
             "g": f32(self.norm.weight), "b": f32(self.norm.bias),
-            "wqk": torch.cat([wq, wk], 0).to(HALF).contiguous(),
+            "wqk": torch.cat([wq, wk], 0).to(half()).contiguous(),
             "bqk": torch.cat([bq, self.k.bias.detach().float()], 0).contiguous(),
             "wv": pack_conv1x1(w16(self.v.weight)),
-            "wo": wo.to(HALF).contiguous(), "bo": bo.contiguous(),
+            "wo": wo.to(half()).contiguous(), "bo": bo.contiguous(),
         }
 
     def _fwd(self, x16, B, H, W):
@@ -185,8 +185,8 @@ class AttnBlock(PackedModule):
         c, n = self.in_channels, H * W
         hn = ops.groupnorm(x16, p["g"], p["b"], batch=B, hw=n, groups=32, eps=1e-6, silu=False)
         qk = ops.gemm(hn, p["wqk"], p["bqk"])                       # [B*n, 2c] = [q / sqrt(c) | k]
-        att = torch.empty((B * n, c), dtype=HALF, device=x16.device)
-        scores = torch.empty((n, n), dtype=HALF, device=x16.device)  # one image at a time (n = 4096: 32 MB)
+        att = torch.empty((B * n, c), dtype=half(), device=x16.device)
+        scores = torch.empty((n, n), dtype=half(), device=x16.device)  # one image at a time (n = 4096: 32 MB)
         for b in range(B):
             rows = slice(b * n, (b + 1) * n)
             ops.gemm(qk[rows, :c], qk[rows, c:], out=scores)        # q k^T (A = q rows, "weights" = k rows)

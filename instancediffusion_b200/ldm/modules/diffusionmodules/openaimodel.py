@@ -27,7 +27,7 @@ import torch.nn as nn
 from .... import ops
 from ....packing import pack_conv1x1, pack_conv3x3
 from ...util import instantiate_from_config
-from .._base import HALF, PackedModule, f32, nchw_to_nhwc16, nhwc16_to_nchw, w16
+from .._base import half, PackedModule, f32, nchw_to_nhwc16, nhwc16_to_nchw, w16
 from ..attention import SpatialTransformer, attention_mask_words
 from .util import zero_module
 
@@ -54,7 +54,7 @@ def Fourier_filter(x_in, threshold, scale):
         raise NotImplementedError("Fourier_filter: only threshold=1 is on the InstanceDiffusion path")
     x16, B, H, W = nchw_to_nhwc16(x_in)
     C = x16.shape[-1]
-    dummy_h = torch.zeros((B * H * W, 8), dtype=HALF, device=x16.device)
+    dummy_h = torch.zeros((B * H * W, 8), dtype=half(), device=x16.device)
     ones = torch.ones(8, dtype=torch.float32, device=x16.device)
     out = ops.scaleu_concat(dummy_h, x16, ones, float(scale), batch=B, height=H, width=W)
     return nhwc16_to_nchw(out[:, 8:], B, H, W, x_in.dtype)
@@ -86,7 +86,7 @@ def _conv3x3_module_forward(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     cin = x16.shape[-1]
     cpad = (cin + 63) // 64 * 64
     if cpad != cin:
-        xp = torch.zeros((x16.shape[0], cpad), dtype=HALF, device=x16.device)
+        xp = torch.zeros((x16.shape[0], cpad), dtype=half(), device=x16.device)
         xp[:, :cin] = x16
         x16 = xp
     wp = _pack_conv3x3_padded(conv.weight, cpad)
@@ -96,8 +96,8 @@ def _conv3x3_module_forward(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
 
 def _pack_conv3x3_padded(weight: torch.Tensor, cin_pad: int) -> torch.Tensor:
     cout, cin = weight.shape[:2]
-    w = torch.zeros((cout, cin_pad, 3, 3), dtype=HALF, device=weight.device)
-    w[:, :cin] = weight.detach().to(HALF)
+    w = torch.zeros((cout, cin_pad, 3, 3), dtype=half(), device=weight.device)
+    w[:, :cin] = weight.detach().to(half())
     return pack_conv3x3(w)
 
 
@@ -216,7 +216,7 @@ class ResBlock(TimestepBlock):
     def _forward(self, x, emb):
         x16, B, H, W = nchw_to_nhwc16(x)
         p = self.pk()
-        e16 = ops.silu(emb.to(HALF).contiguous())
+        e16 = ops.silu(emb.to(half()).contiguous())
         emb_out = ops.gemm(e16, p["we"], p["be"])
         return nhwc16_to_nchw(self._fwd(x16, B, H, W, emb_out), B, H, W, x.dtype)
 
@@ -455,7 +455,7 @@ class UNetModel(PackedModule):
         if hit is not None:
             return hit[1]
         p = self.pk()
-        c16 = context.reshape(-1, context.shape[-1]).to(HALF).contiguous()
+        c16 = context.reshape(-1, context.shape[-1]).to(half()).contiguous()
         kv = ops.gemm(c16, p["w_ctx_all"])
         if len(self._ctx_cache) > 64:
             self._ctx_cache.clear()
@@ -621,6 +621,9 @@ class UNetModel(PackedModule):
     @torch.no_grad()
     def forward_batched(self, inputs: List[dict]) -> List[torch.Tensor]:
         """Run several independent forwards as one batch; returns one eps tensor per input."""
+        if getattr(self, "_storage_epoch", None) != ops.STORAGE_EPOCH:  # storage type switched: derived tensors are stale
+            self._drop_derived()
+            self._storage_epoch = ops.STORAGE_EPOCH
         x, t, ctx, M, okv, n_obj, mask = self._gather_inputs(inputs)
         eps = self._run_core(x, t, ctx, M, okv, n_obj, mask)
         sizes = [inp["x"].shape[0] for inp in inputs]

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from .... import ops
-from .._base import HALF, PackedModule, f32, w16
+from .._base import half, PackedModule, f32, w16
 from .convnext import convnext_tiny
 from .util import FourierEmbedder
 
@@ -83,7 +83,7 @@ class UniFusion(PackedModule):
         p["null_scribble"] = f32(self.null_scribble_feature)
         p["null_polygon"] = f32(self.null_polygon_feature)
         # null seg tokens (segs all zero / dropped): null_seg + pos_embedding (:279-285), 64 rows
-        p["seg_null_in"] = (f32(self.null_seg_feature)[None, :] + f32(self.pos_embedding)[0]).to(HALF).contiguous()
+        p["seg_null_in"] = (f32(self.null_seg_feature)[None, :] + f32(self.pos_embedding)[0]).to(half()).contiguous()
         p["pos"] = f32(self.pos_embedding)[0].contiguous()
         p["w_inconv"] = f32(self.in_conv.weight)
         p["b_inconv"] = f32(self.in_conv.bias)
@@ -133,7 +133,7 @@ class UniFusion(PackedModule):
             D = coords.shape[1]
             if 32 * D != null_pos.numel():
                 raise ValueError(f"UniFusion: modality {idx} expects {null_pos.numel() // 32} coordinates, got {D}")
-            buf = torch.empty((rows, self.in_dim + 32 * D), dtype=HALF, device=dev)
+            buf = torch.empty((rows, self.in_dim + 32 * D), dtype=half(), device=dev)
             ops.fourier_embed(coords, m, null_pos, buf, text=text, null_text=p["null_text"], mask_mode=mode,
                               dropped=dropped)
             toks.append(self._mlp(idx, buf).view(B, N, self.out_dim))

@@ -14,7 +14,45 @@ import torch
 from . import _lib
 from ._lib import AttnArgs, GemmArgs, check
 
+# 16-bit storage type of activations and packed weights: process-wide, fp16 (the reference's autocast type,
+# inference.py:94) unless set_storage_dtype(torch.bfloat16) selects the bf16 build of the library (BASELINE
+# config 3).  Every wrapper below checks its 16-bit operands against it, so tensors of the other type fail
+# loudly instead of being reinterpreted.
 HALF = torch.float16
+STORAGE_EPOCH = 0  # bumped on every switch: weight packs and hoisted tensors built before it are stale
+_KINDS = {torch.float16: "f16", torch.bfloat16: "bf16"}
+
+
+def set_storage_dtype(dtype: torch.dtype) -> None:
+    """Select the 16-bit storage type (torch.float16 or torch.bfloat16) for everything created afterwards.
+    Modules re-pack their weights and the UNet drops its hoisted tensors / captured graphs on next use."""
+    global HALF, STORAGE_EPOCH
+    if dtype not in _KINDS:
+        raise _lib.IdiffError(f"storage dtype must be torch.float16 or torch.bfloat16, got {dtype}")
+    if dtype != HALF:
+        _lib.set_storage(_KINDS[dtype])
+        HALF = dtype
+        STORAGE_EPOCH += 1
+
+
+def storage_dtype() -> torch.dtype:
+    return HALF
+
+
+class storage:
+    """Context manager: `with ops.storage(torch.bfloat16): ...`."""
+
+    def __init__(self, dtype: torch.dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        self.prev = HALF
+        set_storage_dtype(self.dtype)
+        return self
+
+    def __exit__(self, *exc):
+        set_storage_dtype(self.prev)
+        return False
 
 
 # Optional per-launch timing (bench.py's roofline pass): when PROFILE is a list, every wrapper

@@ -18,14 +18,16 @@ import torch
 import torch.distributed as dist
 
 
-def pack_state_dict(sd: Dict[str, torch.Tensor]) -> dict:
+def pack_state_dict(sd: Dict[str, torch.Tensor], dtype: torch.dtype = torch.float16) -> dict:
+    """`dtype`: the 16-bit type the matrices are stored in (pass torch.bfloat16 for a bf16-storage deployment,
+    ops.set_storage_dtype; the slot keeps the name "f16")."""
     index, mats, vecs = [], [], []
     off16 = off32 = 0
     for k, v in sd.items():
         v = v.detach()
         if v.is_floating_point() and v.dim() >= 2:
             index.append((k, tuple(v.shape), "f16", off16, v.numel()))
-            mats.append(v.reshape(-1).to(torch.float16))
+            mats.append(v.reshape(-1).to(dtype))
             off16 += v.numel()
         else:
             index.append((k, tuple(v.shape), "f32", off32, v.numel()))
@@ -33,7 +35,7 @@ def pack_state_dict(sd: Dict[str, torch.Tensor]) -> dict:
             off32 += v.numel()
     dev = next(iter(sd.values())).device
     return {"index": index,
-            "f16": torch.cat(mats) if mats else torch.zeros(0, dtype=torch.float16, device=dev),
+            "f16": torch.cat(mats) if mats else torch.zeros(0, dtype=dtype, device=dev),
             "f32": torch.cat(vecs) if vecs else torch.zeros(0, dtype=torch.float32, device=dev)}
 
 
@@ -66,7 +68,7 @@ def broadcast_pack(pack: dict, src: int = 0) -> int:
     return pack_bytes(pack)
 
 
-def empty_like_pack(module: torch.nn.Module, device) -> dict:
+def empty_like_pack(module: torch.nn.Module, device, dtype: torch.dtype = torch.float16) -> dict:
     """A pack with the index of `module`'s state_dict and uninitialised buffers (the receive side of broadcast_pack)."""
     index, off16, off32 = [], 0, 0
     for k, v in module.state_dict().items():
@@ -76,5 +78,5 @@ def empty_like_pack(module: torch.nn.Module, device) -> dict:
         else:
             index.append((k, tuple(v.shape), "f32", off32, v.numel()))
             off32 += v.numel()
-    return {"index": index, "f16": torch.empty(off16, dtype=torch.float16, device=device),
+    return {"index": index, "f16": torch.empty(off16, dtype=dtype, device=device),
             "f32": torch.empty(off32, dtype=torch.float32, device=device)}

@@ -22,11 +22,12 @@ def test_library_exports_every_declared_symbol():
     declared = set(re.findall(r"\b(idiff_[a-z0-9_]+)\s*\(", header))
     declared -= {"idiff_gemm_args", "idiff_attn_args"}
     assert declared, "no declarations parsed"
-    lib = _lib.load()
-    for name in sorted(declared):
-        assert hasattr(lib, name), f"{name} declared in include/idiff_b200.h but not exported"
+    for kind, code in (("f16", 0), ("bf16", 1)):  # the two storage-type builds of the same sources
+        lib = _lib.load(kind)
+        for name in sorted(declared):
+            assert hasattr(lib, name), f"{name} declared in include/idiff_b200.h but not exported by the {kind} build"
+        assert lib.idiff_version() >= 2 and lib.idiff_storage_dtype() == code
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.idiff_version() >= 1
 
 
 def test_struct_layout_matches_header():

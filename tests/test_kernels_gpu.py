@@ -1,6 +1,8 @@
 """Per-kernel numerics: every C-ABI entry point against a plain torch fp32 reference of the same op
-on the same seeded inputs (the fp16-rounded inputs are upcast, so only accumulation order and the
-fp16 output rounding differ).  Tolerances are stated per test.
+on the same seeded inputs (the 16-bit-rounded inputs are upcast, so only accumulation order and the
+16-bit output rounding differ).  Tolerances are stated per test for fp16 storage; every test runs a
+second time against the bf16-storage build of the library (libidiff_b200_bf16.so) with the tolerances
+scaled by 8 = 2^(11-8), the ratio of the two formats' rounding steps.
 """
 import math
 import os
@@ -17,6 +19,27 @@ def _ops():
     return ops
 
 
+TOL_SCALE = 1.0
+
+
+@pytest.fixture(autouse=True, params=["fp16", "bf16"])
+def storage(request):
+    """Run every test once per storage type of the library."""
+    global TOL_SCALE
+    ops = _ops()
+    bf = request.param == "bf16"
+    ops.set_storage_dtype(torch.bfloat16 if bf else torch.float16)
+    TOL_SCALE = 8.0 if bf else 1.0
+    yield request.param
+    ops.set_storage_dtype(torch.float16)
+    TOL_SCALE = 1.0
+
+
+def _h(t):
+    """To the current 16-bit storage type."""
+    return t.to(_ops().HALF)
+
+
 def _randn(shape, dev, scale=1.0, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     return (torch.randn(shape, generator=g) * scale).to(dev)
@@ -28,7 +51,7 @@ def _check(got, ref, rtol, atol, what):
     assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
     assert torch.isfinite(got).all(), f"{what}: non-finite output"
     err = (got - ref).abs()
-    tol = atol + rtol * ref.abs()
+    tol = TOL_SCALE * (atol + rtol * ref.abs())
     bad = (err > tol)
     max_err = err.max().item()
     ref_max = ref.abs().max().item()
@@ -43,8 +66,8 @@ def _check(got, ref, rtol, atol, what):
                                    (8, 1280, 320), (1024, 1280, 5120), (77, 640, 768)])
 def test_gemm_linear(cuda_device, M, N, K):
     ops = _ops()
-    a = _randn((M, K), cuda_device, 1.0, 1).half()
-    w = _randn((N, K), cuda_device, 1.0 / math.sqrt(K), 2).half()
+    a = _h(_randn((M, K), cuda_device, 1.0, 1))
+    w = _h(_randn((N, K), cuda_device, 1.0 / math.sqrt(K), 2))
     bias = _randn((N,), cuda_device, 0.5, 3)
     out = ops.gemm(a, w, bias)
     ref = a.float() @ w.float().t() + bias
@@ -58,10 +81,10 @@ def test_gemm_stream_k_shapes(cuda_device, M, N, K):
     """Tile counts that are not multiples of the SM count: the ragged waves are split over all SMs in
     k-block units and fixed up through the fp32 workspace; the result must be bit-reproducible."""
     ops = _ops()
-    a = _randn((M, K), cuda_device, 1.0, 1).half()
-    w = _randn((N, K), cuda_device, 1.0 / math.sqrt(K), 2).half()
+    a = _h(_randn((M, K), cuda_device, 1.0, 1))
+    w = _h(_randn((N, K), cuda_device, 1.0 / math.sqrt(K), 2))
     bias = _randn((N,), cuda_device, 0.5, 3)
-    res = _randn((M, N), cuda_device, 1.0, 4).half()
+    res = _h(_randn((M, N), cuda_device, 1.0, 4))
     ref = res.float() + 0.5 * (a.float() @ w.float().t() + bias)
     # the planner may prefer plain rounds for a shape; IDIFF_GEMM_PLAN="0,1" keeps its tile width and
     # forces the stream-K schedule, so both paths are covered
@@ -84,8 +107,8 @@ def test_gemm_geglu_stream_k(cuda_device):
     from instancediffusion_b200.packing import pack_geglu
     ops = _ops()
     M, C = 2048, 1280
-    a = _randn((M, C), cuda_device, 1.0, 1).half()
-    w = _randn((8 * C, C), cuda_device, 1.0 / math.sqrt(C), 2).half()
+    a = _h(_randn((M, C), cuda_device, 1.0, 1))
+    w = _h(_randn((8 * C, C), cuda_device, 1.0 / math.sqrt(C), 2))
     bias = _randn((8 * C,), cuda_device, 0.5, 3)
     wp, bp = pack_geglu(w, bias)
     h = a.float() @ w.float().t() + bias
@@ -103,10 +126,10 @@ def test_gemm_geglu_stream_k(cuda_device):
 def test_gemm_residual_gate_silu(cuda_device):
     ops = _ops()
     M, N, K = 512, 320, 640
-    a = _randn((M, K), cuda_device, 1.0, 1).half()
-    w = _randn((N, K), cuda_device, 1.0 / math.sqrt(K), 2).half()
+    a = _h(_randn((M, K), cuda_device, 1.0, 1))
+    w = _h(_randn((N, K), cuda_device, 1.0 / math.sqrt(K), 2))
     bias = _randn((N,), cuda_device, 0.5, 3)
-    res = _randn((M, N), cuda_device, 1.0, 4).half()
+    res = _h(_randn((M, N), cuda_device, 1.0, 4))
     out = ops.gemm(a, w, bias, residual=res, gate=0.37)
     ref = res.float() + 0.37 * (a.float() @ w.float().t() + bias)
     _check(out, ref, 2e-3, 2e-3, "gemm residual+gate")
@@ -114,7 +137,7 @@ def test_gemm_residual_gate_silu(cuda_device):
     ref = F.silu(a.float() @ w.float().t() + bias)
     _check(out, ref, 2e-3, 2e-3, "gemm silu")
     # per-batch row vector (ResBlock emb add), 4 batches of 128 rows
-    radd = _randn((4, N), cuda_device, 1.0, 5).half()
+    radd = _h(_randn((4, N), cuda_device, 1.0, 5))
     out = ops.gemm(a, w, bias, rowadd=radd, rows_per_batch=128)
     ref = a.float() @ w.float().t() + bias + radd.float().repeat_interleave(128, dim=0)
     _check(out, ref, 2e-3, 2e-3, "gemm rowadd")
@@ -126,8 +149,8 @@ def test_gemm_geglu(cuda_device, M, C):
     from instancediffusion_b200.packing import pack_geglu
     ops = _ops()
     inner = 4 * C
-    a = _randn((M, C), cuda_device, 1.0, 1).half()
-    w = _randn((2 * inner, C), cuda_device, 1.0 / math.sqrt(C), 2).half()
+    a = _h(_randn((M, C), cuda_device, 1.0, 1))
+    w = _h(_randn((2 * inner, C), cuda_device, 1.0 / math.sqrt(C), 2))
     bias = _randn((2 * inner,), cuda_device, 0.5, 3)
     wp, bp = pack_geglu(w, bias)
     out = ops.gemm(a, wp, bp, geglu=True)
@@ -146,8 +169,8 @@ def test_gemm_geglu(cuda_device, M, C):
 def test_conv3x3(cuda_device, B, H, W, Cin, Cout):
     from instancediffusion_b200.packing import pack_conv3x3
     ops = _ops()
-    x = _randn((B, Cin, H, W), cuda_device, 1.0, 1).half()
-    w = _randn((Cout, Cin, 3, 3), cuda_device, 1.0 / math.sqrt(9 * Cin), 2).half()
+    x = _h(_randn((B, Cin, H, W), cuda_device, 1.0, 1))
+    w = _h(_randn((Cout, Cin, 3, 3), cuda_device, 1.0 / math.sqrt(9 * Cin), 2))
     bias = _randn((Cout,), cuda_device, 0.5, 3)
     x_nhwc = x.permute(0, 2, 3, 1).contiguous().reshape(B * H * W, Cin)
     out = ops.gemm(x_nhwc, pack_conv3x3(w), bias, conv=(B, H, W, Cin))
@@ -159,18 +182,18 @@ def test_conv3x3_rowadd_and_nchw_out(cuda_device):
     from instancediffusion_b200.packing import pack_conv3x3
     ops = _ops()
     B, H, W, Cin, Cout = 2, 64, 64, 320, 320
-    x = _randn((B, Cin, H, W), cuda_device, 1.0, 1).half()
-    w = _randn((Cout, Cin, 3, 3), cuda_device, 1.0 / math.sqrt(9 * Cin), 2).half()
+    x = _h(_randn((B, Cin, H, W), cuda_device, 1.0, 1))
+    w = _h(_randn((Cout, Cin, 3, 3), cuda_device, 1.0 / math.sqrt(9 * Cin), 2))
     bias = _randn((Cout,), cuda_device, 0.5, 3)
-    emb = _randn((B, Cout), cuda_device, 1.0, 4).half()
+    emb = _h(_randn((B, Cout), cuda_device, 1.0, 4))
     x_nhwc = x.permute(0, 2, 3, 1).contiguous().reshape(B * H * W, Cin)
     out = ops.gemm(x_nhwc, pack_conv3x3(w), bias, conv=(B, H, W, Cin), rowadd=emb)
     ref = F.conv2d(x.float(), w.float(), bias, padding=1) + emb.float()[:, :, None, None]
     _check(out, ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout), 2e-3, 2e-3, "conv3x3 + emb")
     # final conv 320 -> 4 with fp32 NCHW output (openaimodel.py:461-465)
-    w4 = _randn((4, Cin, 3, 3), cuda_device, 1.0 / math.sqrt(9 * Cin), 5).half()
+    w4 = _h(_randn((4, Cin, 3, 3), cuda_device, 1.0 / math.sqrt(9 * Cin), 5))
     b4 = _randn((4,), cuda_device, 0.5, 6)
-    w4p = torch.zeros((8, 9 * Cin), dtype=torch.float16, device=cuda_device)
+    w4p = torch.zeros((8, 9 * Cin), dtype=_ops().HALF, device=cuda_device)
     w4p[:4] = pack_conv3x3(w4)
     o = torch.empty((B, 4, H, W), dtype=torch.float32, device=cuda_device)
     ops.gemm(x_nhwc, w4p[:4], b4, conv=(B, H, W, Cin), out_nchw=o)
@@ -182,8 +205,8 @@ def test_downsample_and_upsample_helpers(cuda_device):
     from instancediffusion_b200.packing import pack_conv3x3
     ops = _ops()
     B, H, W, C = 2, 32, 32, 320
-    x = _randn((B, C, H, W), cuda_device, 1.0, 1).half()
-    w = _randn((C, C, 3, 3), cuda_device, 1.0 / math.sqrt(9 * C), 2).half()
+    x = _h(_randn((B, C, H, W), cuda_device, 1.0, 1))
+    w = _h(_randn((C, C, 3, 3), cuda_device, 1.0 / math.sqrt(9 * C), 2))
     bias = _randn((C,), cuda_device, 0.5, 3)
     x_nhwc = x.permute(0, 2, 3, 1).contiguous().reshape(B * H * W, C)
     cols = ops.im2col_s2(x_nhwc, B, H, W)
@@ -214,7 +237,7 @@ def test_self_attention_fused_qkv(cuda_device, B, N, d):
     ops = _ops()
     heads = 8
     C = heads * d
-    qkv = _randn((B * N, 3 * C), cuda_device, 1.0, 1).half()
+    qkv = _h(_randn((B * N, 3 * C), cuda_device, 1.0, 1))
     out = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], batch=B, heads=heads, head_dim=d,
                         nq=N, n0=N, scale=d ** -0.5)
     q, k, v = (qkv[:, i * C:(i + 1) * C].reshape(B, N, C) for i in range(3))
@@ -229,9 +252,9 @@ def test_gated_attention_two_segments(cuda_device, B, N, d, shared):
     ops = _ops()
     heads = 8
     C = heads * d
-    qkv = _randn((B * N, 3 * C), cuda_device, 1.0, 1).half()
+    qkv = _h(_randn((B * N, 3 * C), cuda_device, 1.0, 1))
     B1 = 1 if shared else B
-    okv = _randn((B1 * 184, 2 * C), cuda_device, 1.0, 2).half()
+    okv = _h(_randn((B1 * 184, 2 * C), cuda_device, 1.0, 2))
     out = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], batch=B, heads=heads, head_dim=d,
                         nq=N, n0=N, scale=d ** -0.5, k1=okv[:, :C], v1=okv[:, C:], n1=184, kv1_batch=B1)
     q, k, v = (qkv[:, i * C:(i + 1) * C].reshape(B, N, C) for i in range(3))
@@ -246,8 +269,8 @@ def test_cross_attention_77_keys(cuda_device, B, N, d):
     ops = _ops()
     heads = 8
     C = heads * d
-    q = _randn((B * N, C), cuda_device, 1.0, 1).half()
-    kv = _randn((B * 77, 2 * C), cuda_device, 1.0, 2).half()
+    q = _h(_randn((B * N, C), cuda_device, 1.0, 1))
+    kv = _h(_randn((B * 77, 2 * C), cuda_device, 1.0, 2))
     out = ops.attention(q, kv[:, :C], kv[:, C:], batch=B, heads=heads, head_dim=d, nq=N, n0=77, scale=d ** -0.5)
     ref = _ref_attn(q.reshape(B, N, C), kv[:, :C].reshape(B, 77, C), kv[:, C:].reshape(B, 77, C), heads, d ** -0.5)
     _check(out, ref, 3e-3, 3e-3, f"cross-attn B{B} N{N} d{d}")
@@ -260,7 +283,7 @@ def test_cross_attention_77_keys(cuda_device, B, N, d):
                                              (2, 256, 1280, False, 1e-6), (1, 1024, 1920, True, 1e-5)])
 def test_groupnorm(cuda_device, B, HW, C, silu, eps):
     ops = _ops()
-    x = (_randn((B * HW, C), cuda_device, 1.5, 1) + 0.3).half()
+    x = _h((_randn((B * HW, C), cuda_device, 1.5, 1) + 0.3))
     gamma = 1.0 + _randn((C,), cuda_device, 0.2, 2)
     beta = _randn((C,), cuda_device, 0.2, 3)
     out = ops.groupnorm(x, gamma, beta, batch=B, hw=HW, groups=32, eps=eps, silu=silu)
@@ -280,7 +303,7 @@ def test_groupnorm_single_pass(cuda_device, B, HW, C):
     shared memory) at every GroupNorm shape of the UNet; it must agree with torch and, to fp32
     summation-order noise, with the two-kernel default."""
     ops = _ops()
-    x = (_randn((B * HW, C), cuda_device, 1.5, 1) + 0.3).half()
+    x = _h((_randn((B * HW, C), cuda_device, 1.5, 1) + 0.3))
     gamma = 1.0 + _randn((C,), cuda_device, 0.2, 2)
     beta = _randn((C,), cuda_device, 0.2, 3)
     base = ops.groupnorm(x, gamma, beta, batch=B, hw=HW, groups=32, eps=1e-5, silu=True)
@@ -300,7 +323,7 @@ def test_groupnorm_single_pass(cuda_device, B, HW, C):
 @pytest.mark.parametrize("rows,C", [(4096, 320), (1000, 640), (77, 1280)])
 def test_layernorm(cuda_device, rows, C):
     ops = _ops()
-    x = (_randn((rows, C), cuda_device, 1.5, 1) + 0.3).half()
+    x = _h((_randn((rows, C), cuda_device, 1.5, 1) + 0.3))
     gamma = 1.0 + _randn((C,), cuda_device, 0.2, 2)
     beta = _randn((C,), cuda_device, 0.2, 3)
     out = ops.layernorm(x, gamma, beta, 1e-5)
@@ -326,8 +349,8 @@ def _fourier_filter_ref(x, threshold, scale):
 @pytest.mark.parametrize("B,H,W,C1,C2", [(2, 8, 8, 1280, 1280), (2, 16, 16, 1280, 640), (1, 64, 64, 320, 320), (1, 24, 24, 64, 64)])
 def test_scaleu_concat(cuda_device, B, H, W, C1, C2):
     ops = _ops()
-    h = _randn((B, C1, H, W), cuda_device, 1.0, 1).half()
-    skip = (_randn((B, C2, H, W), cuda_device, 1.0, 2) + 0.5).half()
+    h = _h(_randn((B, C1, H, W), cuda_device, 1.0, 1))
+    skip = _h((_randn((B, C2, H, W), cuda_device, 1.0, 2) + 0.5))
     b_param = _randn((C1,), cuda_device, 0.5, 3)
     s_param = 0.4
     b1 = torch.tanh(b_param) + 1
@@ -350,8 +373,8 @@ def test_layout_roundtrip(cuda_device):
     y = ops.nchw_f32_to_nhwc_f16(x, 64)
     ref = torch.zeros((3 * 4096, 64), device=cuda_device)
     ref[:, :4] = x.permute(0, 2, 3, 1).reshape(-1, 4)
-    _check(y, ref.half(), 0, 0, "nchw->nhwc pad")
-    z = _randn((2 * 256, 320), cuda_device, 1.0, 2).half()
+    _check(y, _h(ref), 0, 0, "nchw->nhwc pad")
+    z = _h(_randn((2 * 256, 320), cuda_device, 1.0, 2))
     back = ops.nhwc_f16_to_nchw_f32(z, 2, 16, 16)
     _check(back, z.float().view(2, 256, 320).permute(0, 2, 1).reshape(2, 320, 16, 16), 0, 0, "nhwc->nchw")
 
@@ -379,7 +402,7 @@ def test_fourier_embed(cuda_device, D, mode, dropped):
     text = _randn((rows, 768), cuda_device, 1.0, 2)
     null_text = _randn((768,), cuda_device, 1.0, 3)
     null_pos = _randn((32 * D,), cuda_device, 1.0, 4)
-    out = torch.empty((rows, 768 + 32 * D), dtype=torch.float16, device=cuda_device)
+    out = torch.empty((rows, 768 + 32 * D), dtype=_ops().HALF, device=cuda_device)
     ops.fourier_embed(coords, masks, null_pos, out, text=text, null_text=null_text, mask_mode=mode, dropped=dropped)
     freqs = 100 ** (torch.arange(16, device=cuda_device) / 16)
     emb = torch.cat([f(fr * coords) for fr in freqs for f in (torch.sin, torch.cos)], -1)
@@ -421,8 +444,8 @@ def test_plms_update_and_mean(cuda_device):
 def test_gemm_gelu_epilogue_small_k_n(cuda_device, M, N, K):
     """pwconv1 (GELU fused) and the patchify GEMMs: N < one tile, K = 48 < one 64-wide k-block."""
     ops = _ops()
-    a = _randn((M, K), cuda_device, 1.0, 1).half()
-    w = _randn((N, K), cuda_device, 1.0 / math.sqrt(K), 2).half()
+    a = _h(_randn((M, K), cuda_device, 1.0, 1))
+    w = _h(_randn((N, K), cuda_device, 1.0 / math.sqrt(K), 2))
     bias = _randn((N,), cuda_device, 0.5, 3)
     ref = F.gelu(a.float() @ w.float().t() + bias)
     _check(ops.gemm(a, w, bias, gelu=True), ref, 2e-3, 2e-3, f"gemm+gelu {M}x{N}x{K}")
@@ -432,7 +455,7 @@ def test_gemm_gelu_epilogue_small_k_n(cuda_device, M, N, K):
 @pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 96), (1, 128, 128, 96), (2, 8, 8, 768), (1, 5, 7, 192)])
 def test_dwconv7x7(cuda_device, B, H, W, C):
     ops = _ops()
-    x = _randn((B, C, H, W), cuda_device, 1.0, 4).half()
+    x = _h(_randn((B, C, H, W), cuda_device, 1.0, 4))
     w = _randn((C, 1, 7, 7), cuda_device, 1.0 / 7, 5)
     b = _randn((C,), cuda_device, 0.1, 6)
     ref = F.conv2d(x.float(), w, b, padding=3, groups=C).permute(0, 2, 3, 1).reshape(B * H * W, C)
@@ -444,7 +467,7 @@ def test_dwconv7x7(cuda_device, B, H, W, C):
 @pytest.mark.parametrize("B,H,W,C,p", [(2, 16, 16, 3, 4), (1, 8, 8, 96, 2), (2, 4, 12, 384, 2)])
 def test_patchify(cuda_device, B, H, W, C, p):
     ops = _ops()
-    x = _randn((B, H, W, C), cuda_device, 1.0, 7).half()
+    x = _h(_randn((B, H, W, C), cuda_device, 1.0, 7))
     out = ops.patchify(x.reshape(B * H * W, C), B, H, W, C, p)
     ref = x.view(B, H // p, p, W // p, p, C).permute(0, 1, 3, 2, 4, 5).reshape(B * (H // p) * (W // p), p * p * C)
     assert torch.equal(out, ref)
@@ -471,9 +494,9 @@ def test_segs_inconv_and_seg_tokens(cuda_device, S):
     _check(y0, b.view(1, 3).expand(B * R * R, 3), 1e-3, 1e-3, "segs_inconv zero view")
     # token reinterpretation: reshape(B, -1, T).permute(0, 2, 1) of the NCHW feature map
     P, C, T = 256, 768, 64
-    feat = _randn((B, C, 16, 16), cuda_device, 1.0, 10).half()
+    feat = _h(_randn((B, C, 16, 16), cuda_device, 1.0, 10))
     pos = _randn((T, C * P // T), cuda_device, 0.5, 11)
-    null_pos = _randn((T, C * P // T), cuda_device, 1.0, 12).half()
+    null_pos = _h(_randn((T, C * P // T), cuda_device, 1.0, 12))
     nhwc = feat.permute(0, 2, 3, 1).reshape(B * P, C).contiguous()
     out = ops.seg_tokens(nhwc, null_pos, pos, seg_sum, B, P, T).view(B, T, -1)
     ref0 = feat.float().reshape(B, -1, T).permute(0, 2, 1)[0] + pos
@@ -491,10 +514,10 @@ def test_gemm_layernorm_fold(cuda_device, M, C, mean_shift):
     LayerNorm / linear on the fp16 x the producer stored.  Also: the statistics themselves, and the one-slot
     row_stats entry point."""
     ops = _ops()
-    a = _randn((M, C), cuda_device, 1.0, 1).half()
-    w0 = _randn((C, C), cuda_device, 1.0 / math.sqrt(C), 2).half()
+    a = _h(_randn((M, C), cuda_device, 1.0, 1))
+    w0 = _h(_randn((C, C), cuda_device, 1.0 / math.sqrt(C), 2))
     b0 = _randn((C,), cuda_device, 0.5, 3) + mean_shift
-    res = _randn((M, C), cuda_device, 1.0, 4).half()
+    res = _h(_randn((M, C), cuda_device, 1.0, 4))
     x, st = ops.gemm(a, w0, b0, residual=res, gate=0.7, want_stats=True)
     xf = x.float()
     # statistics: sum over slots == row sums of the stored x (up to fp16 rounding of x: the epilogue sums fp32)
@@ -532,10 +555,10 @@ def test_gemm_stats_from_long_k_producer(cuda_device):
     """FF out-projection at C=1280 (K = 5120 > 2560): the 8-warp direct epilogue also leaves row statistics."""
     ops = _ops()
     M, C, K = 2048, 1280, 5120
-    a = _randn((M, K), cuda_device, 1.0, 1).half()
-    w = _randn((C, K), cuda_device, 1.0 / math.sqrt(K), 2).half()
+    a = _h(_randn((M, K), cuda_device, 1.0, 1))
+    w = _h(_randn((C, K), cuda_device, 1.0 / math.sqrt(K), 2))
     b = _randn((C,), cuda_device, 0.5, 3)
-    res = _randn((M, C), cuda_device, 1.0, 4).half()
+    res = _h(_randn((M, C), cuda_device, 1.0, 4))
     x, st = ops.gemm(a, w, b, residual=res, want_stats=True)
     xf = x.float()
     _check(st.t[:, :, 0].sum(0), xf.sum(1), 1e-3, 0.1, "long-K stats sum")
