@@ -169,6 +169,24 @@ def cpu_forward_seconds(n_forwards: int = 2, threads: int | None = None):
     return dt, threads
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write banners there (NCCL prints its version on
+    communicator creation): point fd 1 at stderr for the duration of the run and keep the real stdout for the line."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def run_reference_arm(args):
     """`--impl reference`: the reference's CPU implementation of the path (the oracle port of its
     forward; the Python reference itself cannot travel to the GPU box), all host threads.  Each
@@ -199,7 +217,7 @@ def run_reference_arm(args):
                                    f"{t_fwd:.2f} s each, x{fpc} forwards per image (extrapolated)"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -378,6 +396,7 @@ def main():
                     help="16-bit storage type (default: the config's own -- fp16, bf16 for config 4)")
     ap.add_argument("--no-mis-leg", action="store_true", help="skip the extra mis=0.36 leg of config 2")
     args = ap.parse_args()
+    _claim_stdout()
     cfg = CONFIGS[args.config]
     WORKLOAD, BATCH, N_INST, FLAVOR, LATENT = cfg["workload"], cfg["batch"], cfg["n"], cfg["flavor"], cfg["latent"]
     if args.mis is None:
@@ -521,7 +540,7 @@ def main():
         except Exception as exc:  # the baseline must never take the bench line down
             line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {exc!r}"}
-    print(json.dumps(line))
+    _emit(line)
 
 
 if __name__ == "__main__":

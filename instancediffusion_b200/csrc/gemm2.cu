@@ -186,6 +186,39 @@ IDIFF_DEVICE uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   return r;
 }
+IDIFF_DEVICE uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// value * gelu(gate) for two elements at once: gelu_erf_f (common.cuh) restated on packed pairs.  With
+// a = |g|, z = a / sqrt 2, pe = poly(t) * exp(-z^2) = 1 - erf(z):  gelu(g) = 0.5 * ((g + a) - a * pe)
+// (g + a is exactly 2g or 0, so the negative side has no cancellation).  Per pair: 2 LOP, 13 packed FP
+// ops and 4 MUFU against ~36 scalar instructions: the K = 320 GEGLU projection was bound by its epilogue's
+// issue slots (ncu: issue 47 %, XU 31 %, tensor 37 %; profiles/r2_ncu_geglu320.summary.csv).
+IDIFF_DEVICE uint64_t geglu_f2(uint64_t val, uint64_t g) {
+  float g0, g1;
+  f2_unpack(g, g0, g1);
+  const uint64_t a = f2_pack(fabsf(g0), fabsf(g1));
+  const uint64_t z = f2_mul(a, f2_pack(0.70710678118654752f, 0.70710678118654752f));
+  float d0, d1, t0, t1;
+  f2_unpack(f2_fma(z, f2_pack(0.3275911f, 0.3275911f), f2_pack(1.0f, 1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t = f2_pack(t0, t1);
+  uint64_t poly = f2_fma(t, f2_pack(1.061405429f, 1.061405429f), f2_pack(-1.453152027f, -1.453152027f));
+  poly = f2_fma(poly, t, f2_pack(1.421413741f, 1.421413741f));
+  poly = f2_fma(poly, t, f2_pack(-0.284496736f, -0.284496736f));
+  poly = f2_fma(poly, t, f2_pack(0.254829592f, 0.254829592f));
+  poly = f2_mul(poly, t);
+  float x0, x1, e0, e1;
+  f2_unpack(f2_mul(f2_mul(z, z), f2_pack(-1.4426950408889634f, -1.4426950408889634f)), x0, x1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+  const uint64_t pe = f2_mul(poly, f2_pack(e0, e1));
+  const uint64_t two_gelu = f2_fma(f2_mul(a, f2_pack(-1.0f, -1.0f)), pe, f2_add(g, a));  // (g + a) - a * pe
+  return f2_mul(f2_mul(val, f2_pack(0.5f, 0.5f)), two_gelu);
+}
 IDIFF_DEVICE void lds_f2x2(uint32_t a, uint64_t& p0, uint64_t& p1) {  // four floats as two packed pairs
   asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];\n" : "=l"(p0), "=l"(p1) : "r"(a));
 }
@@ -306,13 +339,7 @@ IDIFF_DEVICE void epi_chunks_geglu(uint32_t trow, uint32_t tab_s, uint32_t row_s
         gv[1] = f2_add(gv[1], bg1);
       }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float a0, a1, g0, g1;
-        f2_unpack(xv[h], a0, a1);
-        f2_unpack(gv[h], g0, g1);
-        x[4 * q + 2 * h] = a0 * gelu_erf_f(g0);
-        x[4 * q + 2 * h + 1] = a1 * gelu_erf_f(g1);
-      }
+      for (int h = 0; h < 2; ++h) f2_unpack(geglu_f2(xv[h], gv[h]), x[4 * q + 2 * h], x[4 * q + 2 * h + 1]);
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {  // GEGLU boxes are 64 columns wide: SWIZZLE_128B
