@@ -36,33 +36,41 @@ struct AttnKParams {
   int out_ld;
 };
 
-template <int D>
+// KV = keys per tile.  64 keeps the footprint of head_dim 80 at 112 KiB of shared memory and 256 TMEM
+// columns, so two CTAs are resident per SM and cover each other's softmax / hand-off latency (what took
+// attention2 from 566 to 414 us); 128 is the one-CTA-per-SM layout (IDIFF_ATT_BKV=128 for A/B runs).
+template <int D, int KV>
 struct AttnCfg {
   static constexpr int ND = (D + 63) / 64;           // 64-wide d chunks (one TMA box each)
   static constexpr int KSTEPS = (D + 15) / 16;       // UMMA k-steps of QK^T (zero padded)
-  static constexpr int BKV = (D > 128) ? 64 : 128;   // keys per tile
+  static constexpr int BKV = KV;                     // keys per tile
   static constexpr int DV = ND * 64;                 // UMMA N of the PV product
   static constexpr int STAGES = (D <= 64) ? 3 : 2;
   static constexpr int Q_BYTES = ND * BQ * 128;
   static constexpr int KV_TILE_BYTES = ND * BKV * 128;  // one of K or V
   static constexpr int P_BYTES = (BKV / 64) * BQ * 128;
-  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_TILE_BYTES + P_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_TILE_BYTES + P_BYTES + 256;  // (no alignment slack)
   static constexpr int TMEM_S0 = 0;
   static constexpr int TMEM_S1 = BKV;
   static constexpr int TMEM_O = 2 * BKV;
+  static constexpr int TMEM_COLS = (2 * BKV + DV <= 256) ? 256 : 512;
   static_assert(2 * BKV + DV <= 512, "TMEM budget");
+  // two CTAs per SM: 228 KiB per SM, 1 KiB reserved per CTA
+  static constexpr int MIN_CTAS = (SMEM_BYTES <= 113 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
 };
 
-template <int D>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int D, int KV>
+__global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D, KV>::MIN_CTAS)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                  const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                  const __grid_constant__ CUtensorMap tmV1, const AttnKParams p) {
-  using Cfg = AttnCfg<D>;
+  using Cfg = AttnCfg<D, KV>;
   constexpr int ND = Cfg::ND, BKV = Cfg::BKV, STAGES = Cfg::STAGES, DV = Cfg::DV;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {  // SWIZZLE_128B tiles need it; no slack is budgeted (see Cfg)
+    if (threadIdx.x == 0) printf("idiff: attention shared memory base not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::Q_BYTES;
   uint8_t* sV = sK + STAGES * Cfg::KV_TILE_BYTES;
@@ -102,7 +110,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -301,7 +309,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -315,9 +323,9 @@ static int make_head_tmap(CUtensorMap* m, const void* base, int d, int heads, in
   return encode_tmap_f16(m, base, 4, dims, strides, box);
 }
 
-template <int D>
+template <int D, int KV>
 static int launch_attention(const idiff_attn_args* a, cudaStream_t stream) {
-  using Cfg = AttnCfg<D>;
+  using Cfg = AttnCfg<D, KV>;
   CUtensorMap tmQ, tmK0, tmV0, tmK1, tmV1;
   if (make_head_tmap(&tmQ, a->q, D, a->heads, a->nq, a->batch, a->q_ld, BQ)) return -1;
   if (make_head_tmap(&tmK0, a->k0, D, a->heads, a->n0, a->batch, a->k0_ld, Cfg::BKV)) return -1;
@@ -341,13 +349,13 @@ static int launch_attention(const idiff_attn_args* a, cudaStream_t stream) {
   p.out_ld = a->out_ld;
   static bool attr_set = false;
   if (!attr_set) {
-    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<D>,
+    IDIFF_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<D, KV>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           Cfg::SMEM_BYTES));
     attr_set = true;
   }
   dim3 grid((a->nq + BQ - 1) / BQ, a->heads, a->batch);
-  IDIFF_CHECK_CUDA(launch_pdl(attention_kernel<D>, dim3(grid), dim3(ATT_THREADS), Cfg::SMEM_BYTES, stream, tmQ, tmK0, tmV0, tmK1, tmV1, p));
+  IDIFF_CHECK_CUDA(launch_pdl(attention_kernel<D, KV>, dim3(grid), dim3(ATT_THREADS), Cfg::SMEM_BYTES, stream, tmQ, tmK0, tmV0, tmK1, tmV1, p));
   IDIFF_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -379,10 +387,16 @@ extern "C" int idiff_attention(const idiff_attn_args* a, void* stream) {
         const char* e = getenv("IDIFF_ATTN_V1");
         return e && e[0] == '1';
       }();
-      return use_v1 ? launch_attention<40>(a, s) : att2::attention_v2_d40(a, s);
+      return use_v1 ? launch_attention<40, 128>(a, s) : att2::attention_v2_d40(a, s);
     }
-    case 80: return launch_attention<80>(a, s);
-    case 160: return launch_attention<160>(a, s);
+    case 80: {
+      static const bool wide = []() {
+        const char* e = getenv("IDIFF_ATT_BKV");
+        return e && atoi(e) == 128;
+      }();
+      return wide ? launch_attention<80, 128>(a, s) : launch_attention<80, 64>(a, s);
+    }
+    case 160: return launch_attention<160, 64>(a, s);
     default: return set_error("idiff_attention: unsupported head_dim %d (40/80/160)", a->head_dim);
   }
 }

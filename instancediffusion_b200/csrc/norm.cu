@@ -215,7 +215,7 @@ gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float*
 }
 
 // ---------------------------------------------------------------------------------------------
-// Single-pass GroupNorm (opt-in, IDIFF_GN_FUSED=1; not yet the default).  One thread-block cluster per
+// Single-pass GroupNorm (the default where one wave holds the whole launch).  One thread-block cluster per
 // (sample, slab of CS channels = whole groups): every CTA of the cluster streams its share of the
 // pixels once from global memory into shared memory while accumulating per-channel sums, the
 // per-group partial sums of the CL CTAs are exchanged through distributed shared memory and added in
@@ -590,8 +590,11 @@ extern "C" int idiff_groupnorm(const void* x, void* y, const float* gamma, const
   IDIFF_REQUIRE(channels % 8 == 0 && channels <= 4096, "idiff_groupnorm: C=%d must be a multiple of 8, <= 4096", channels);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   {
-    const char* fe = getenv("IDIFF_GN_FUSED");  // read per call so tests can cover both paths
-    const bool fused_on = fe && fe[0] == '1';
+    // Single-pass cluster kernel wherever the launch fits one wave (gn_fused_geometry): measured 42 -> 31 us at
+    // 4096x320, 36 -> 21 at 1024x640, 26 -> 16 at 256x1280, 22 -> 12 at 64x1280 (batch 8; profiles/README.md);
+    // IDIFF_GN_FUSED=0 forces the two-kernel path (read per call so tests can cover both).
+    const char* fe = getenv("IDIFF_GN_FUSED");
+    const bool fused_on = !(fe && fe[0] == '0');
     int CS, CL, kf;
     size_t smem_f;
     if (fused_on && gn_fused_geometry(batch, hw, channels, groups, &CS, &CL, &kf, &smem_f)) {

@@ -281,12 +281,19 @@ def test_cross_attention_77_keys(cuda_device, B, N, d):
 # --------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,HW,C,silu,eps", [(2, 4096, 320, True, 1e-5), (2, 1024, 960, True, 1e-5), (3, 64, 2560, True, 1e-5),
                                              (2, 256, 1280, False, 1e-6), (1, 1024, 1920, True, 1e-5)])
-def test_groupnorm(cuda_device, B, HW, C, silu, eps):
+@pytest.mark.parametrize("two_kernel", [False, True])
+def test_groupnorm(cuda_device, B, HW, C, silu, eps, two_kernel):
+    """Default dispatch (single-pass cluster kernel where the launch fits one wave) and the forced two-kernel path."""
     ops = _ops()
     x = _h((_randn((B * HW, C), cuda_device, 1.5, 1) + 0.3))
     gamma = 1.0 + _randn((C,), cuda_device, 0.2, 2)
     beta = _randn((C,), cuda_device, 0.2, 3)
-    out = ops.groupnorm(x, gamma, beta, batch=B, hw=HW, groups=32, eps=eps, silu=silu)
+    if two_kernel:
+        os.environ["IDIFF_GN_FUSED"] = "0"
+    try:
+        out = ops.groupnorm(x, gamma, beta, batch=B, hw=HW, groups=32, eps=eps, silu=silu)
+    finally:
+        os.environ.pop("IDIFF_GN_FUSED", None)
     xr = x.float().view(B, HW, C).permute(0, 2, 1)
     ref = F.group_norm(xr, 32, gamma, beta, eps)
     if silu:
@@ -299,20 +306,20 @@ def test_groupnorm(cuda_device, B, HW, C, silu, eps):
                                     (8, 1024, 1920), (8, 1024, 960), (8, 256, 1280), (8, 256, 2560), (8, 256, 1920),
                                     (8, 64, 1280), (8, 64, 2560), (2, 4096, 320), (1, 256, 1280)])
 def test_groupnorm_single_pass(cuda_device, B, HW, C):
-    """The opt-in cluster kernel (IDIFF_GN_FUSED=1: one pass, statistics exchanged through distributed
-    shared memory) at every GroupNorm shape of the UNet; it must agree with torch and, to fp32
-    summation-order noise, with the two-kernel default."""
+    """The single-pass cluster kernel (one pass, statistics exchanged through distributed shared memory; the
+    default for shapes that fit one wave, IDIFF_GN_FUSED=0 forces the two-kernel path) at every GroupNorm
+    shape of the UNet; it must agree with torch and, to fp32 summation-order noise, with the two-kernel path."""
     ops = _ops()
     x = _h((_randn((B * HW, C), cuda_device, 1.5, 1) + 0.3))
     gamma = 1.0 + _randn((C,), cuda_device, 0.2, 2)
     beta = _randn((C,), cuda_device, 0.2, 3)
-    base = ops.groupnorm(x, gamma, beta, batch=B, hw=HW, groups=32, eps=1e-5, silu=True)
-    os.environ["IDIFF_GN_FUSED"] = "1"
+    os.environ["IDIFF_GN_FUSED"] = "0"
     try:
-        out = ops.groupnorm(x, gamma, beta, batch=B, hw=HW, groups=32, eps=1e-5, silu=True)
-        again = ops.groupnorm(x, gamma, beta, batch=B, hw=HW, groups=32, eps=1e-5, silu=True)
+        base = ops.groupnorm(x, gamma, beta, batch=B, hw=HW, groups=32, eps=1e-5, silu=True)
     finally:
         os.environ.pop("IDIFF_GN_FUSED", None)
+    out = ops.groupnorm(x, gamma, beta, batch=B, hw=HW, groups=32, eps=1e-5, silu=True)
+    again = ops.groupnorm(x, gamma, beta, batch=B, hw=HW, groups=32, eps=1e-5, silu=True)
     ref = F.silu(F.group_norm(x.float().view(B, HW, C).permute(0, 2, 1), 32, gamma, beta, 1e-5))
     ref = ref.permute(0, 2, 1).reshape(B * HW, C)
     _check(out, ref, 2e-3, 2e-3, f"single-pass groupnorm B{B} HW{HW} C{C}")
