@@ -69,8 +69,11 @@ def w16(p: torch.Tensor) -> torch.Tensor:
 
 
 def f32(p: torch.Tensor) -> torch.Tensor:
+    """fp32 *copy* for a pack.  (`.float()` of an fp32 parameter is the parameter itself: a pack entry aliasing it
+    silently followed an in-place load_state_dict of a plain nn.Conv2d -- undo_first_conv_restore -- and the cached
+    SD-first-conv pack carried the other conv's bias from the second sample() call on.)"""
     dev_of(p)
-    return p.detach().float().contiguous()
+    return p.detach().to(dtype=torch.float32, copy=True).contiguous()
 
 
 def to_tokens(x: torch.Tensor):

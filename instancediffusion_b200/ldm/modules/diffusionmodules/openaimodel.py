@@ -364,7 +364,9 @@ class UNetModel(PackedModule):
         """Not in the reference (whose swap is permanent within a process): lets a long-lived server /
         the benchmark run several `sample()` calls on one model object."""
         if getattr(self, "_first_conv_restored", False):
-            self.input_blocks[0][0].load_state_dict(self.first_conv_state_dict)
+            conv = conv_nd(2, 4, 320, 3, padding=1)  # a new module: packs built from the SD conv keep their tensors
+            conv.load_state_dict(self.first_conv_state_dict)
+            self.input_blocks[0][0] = conv.to(self.input_blocks[0][0].weight.device)
             self._first_conv_restored = False
 
     def _in_conv_pack(self):

@@ -25,7 +25,7 @@ pytestmark = pytest.mark.gpu
 EPS_TOL_BF16 = 3e-2
 LATENT_TOL_BF16 = 3.7e-2
 ENVELOPE_FACTOR = 1.25
-ENVELOPE_FACTOR_LATENT = 2.0
+ENVELOPE_FACTOR_LATENT = 1.25
 
 
 @pytest.fixture(scope="module")

@@ -191,7 +191,7 @@ def test_sampler_latent_vs_reference_golden(cuda_device, unet, name):
     """End-to-end latent after the full PLMS / Multi-instance loop (config 1 of BASELINE.json for
     mis_S10).  north_star's rtol=1e-3/atol=1e-4 on the latent is tighter than fp16 re-association
     noise compounded over 10-30 CFG-7.5 forwards (measured for the reference's own arithmetic under
-    autocast(fp16) in tests/test_parity_r2_gpu.py); the bound held here is 8e-3 relative L2 vs the fp32
+    autocast(fp16) in tests/test_parity_r2_gpu.py); the bound held here is 7.4e-3 relative L2 vs the fp32
     reference = 2x the measured value, which is printed."""
     from functools import partial
     from instancediffusion_b200 import synthetic
@@ -224,4 +224,4 @@ def test_sampler_latent_vs_reference_golden(cuda_device, unet, name):
         unet.restore_first_conv_from_SD = orig
         unet.undo_first_conv_restore()
         set_alpha_scale(unet, 1)
-    _report(x, gold[name], f"sampler/{name}", 8e-3, 5e-2)  # measured 2.8-3.7e-3
+    _report(x, gold[name], f"sampler/{name}", 7.4e-3, 5e-2)  # <= 2x measured: 2.8e-3 (MIS S=10) / 3.7e-3 (PLMS S=4)
