@@ -1410,8 +1410,12 @@ static Plan plan_gemm(const idiff_gemm_args* a, int fixed_bn) {  // fixed_bn: 0 
     const long pad = (long)((a->N + bn - 1) / bn) * bn;
     if (!fixed_bn && pad > min_pad + min_pad / 14) continue;  // more than ~7 % wasted columns
     const long T = (long)((a->N + bn - 1) / bn) * m_tiles;
-    const double t_kb = fmax(2.0 * bn, (16384.0 + 128.0 * bn) / 50.0);
-    const double t_epi = 1000.0 * bn / 32.0;
+    // constants refitted in round 2 against tools/plan_sweep.py (every linear / conv shape of the forward x
+    // {128,160,192,256} x {rounds, stream-K}: the model's picks cost 9.40 ms per forward against 9.28 for the
+    // per-shape optimum and 9.52 with the round-1 constants): operand ring ~80 B/clk/SM, epilogue ~47 clk per
+    // output column, stream-K fixed cost ~20k clk
+    const double t_kb = fmax(2.0 * bn, (16384.0 + 128.0 * bn) / 80.0);
+    const double t_epi = 1500.0 * bn / 32.0;
     const double t_tile = KB * t_kb + 600.0;
     const long rounds = (T + sms - 1) / sms;
     const double cost_dp = rounds * t_tile + t_epi;
@@ -1424,7 +1428,7 @@ static Plan plan_gemm(const idiff_gemm_args* a, int fixed_bn) {  // fixed_bn: 0 
       const long t_dp = full >= 2 ? (full - 1) * sms : 0;
       const long t_sk = T - t_dp;
       const double followers = t_sk < sms ? (double)(sms - t_sk) / t_sk : 1.0;
-      const double cost_sk = (full >= 2 ? (full - 1) : 0) * t_tile + (double)t_sk * KB / sms * t_kb + t_epi + 30000.0 +
+      const double cost_sk = (full >= 2 ? (full - 1) : 0) * t_tile + (double)t_sk * KB / sms * t_kb + t_epi + 20000.0 +
                              followers * 128.0 * bn * 4.0 / 40.0;
       if (cost_sk < best_cost) {
         best_cost = cost_sk;
