@@ -316,6 +316,7 @@ class UNetModel(PackedModule):
         # hoisted, step-invariant tensors (keyed caches)
         self._ctx_cache: Dict = {}
         self._obj_cache: Dict = {}
+        self._cat_cache: Dict = {}
         self._graphs: Dict = {}
         self._in_packs: Dict = {}
         self.use_cuda_graph = os.environ.get("IDIFF_CUDA_GRAPH", "1") != "0"
@@ -387,6 +388,7 @@ class UNetModel(PackedModule):
             self._graphs.clear()
             self._ctx_cache.clear()
             self._obj_cache.clear()
+            self._cat_cache.clear()
 
     def _apply(self, fn, *a, **k):
         self._drop_derived()
@@ -496,6 +498,7 @@ class UNetModel(PackedModule):
     def clear_caches(self):
         self._ctx_cache.clear()
         self._obj_cache.clear()
+        self._cat_cache.clear()
         self._graphs.clear()
 
     # ------------------------------------------------------------------------------------------
@@ -574,13 +577,17 @@ class UNetModel(PackedModule):
         return eps
 
     def _gather_inputs(self, inputs: List[dict]):
-        """Concatenate independent forwards (cond / uncond / MIS trajectories) along the batch."""
-        xs, ts, ctxs, okv_lists, masks = [], [], [], [], []
+        """Concatenate independent forwards (cond / uncond / MIS trajectories) along the batch.  The step-invariant
+        parts -- text K/V, per-fuser object K/V, mask words -- are concatenated once per combination of inputs and
+        reused on every later step (the same tensor objects come back, which lets `_CoreGraph.replay` skip its copies
+        as well): 17-19 torch.cat launches and as many copies per forward otherwise (profiles/README.md round 2)."""
+        xs, ts, ctxs, okv_lists, masks, bs = [], [], [], [], [], []
         active = self._fusers_active()
         n_obj = 0
         for inp in inputs:
             x = inp["x"]
             b = x.shape[0]
+            bs.append(b)
             xs.append(x.float())
             ts.append(inp["timesteps"].float().reshape(-1).expand(b) if inp["timesteps"].numel() == 1
                       else inp["timesteps"].float())
@@ -592,12 +599,29 @@ class UNetModel(PackedModule):
                     raise ValueError(f"inputs of one batched forward carry different object-token counts "
                                      f"({n_obj} vs {n_obj_i}); prepare() them with the same max_box")
                 n_obj = n_obj_i
-                if Bo != b:
-                    if Bo != 1:
-                        raise ValueError(f"grounding batch {Bo} does not match latent batch {b}")
-                    kvs = [kv.view(1, n_obj, -1).expand(b, n_obj, kv.shape[-1]).reshape(b * n_obj, -1) for kv in kvs]
-                okv_lists.append(kvs)
+                if Bo != b and Bo != 1:
+                    raise ValueError(f"grounding batch {Bo} does not match latent batch {b}")
+                okv_lists.append((kvs, Bo))
         M = inputs[0]["context"].shape[1]
+        x = xs[0].contiguous() if len(inputs) == 1 else torch.cat(xs, 0)
+        t = ts[0].contiguous() if len(inputs) == 1 else torch.cat(ts, 0)
+        # the hoisted tensors above are cached objects: their identities (and the batch sizes) name the combination
+        key = (active, tuple(bs), tuple(id(c) for c in ctxs), tuple(id(k) for k, _ in okv_lists),
+               tuple(id(m) for m, _ in masks))
+        hit = self._cat_cache.get(key)
+        if hit is not None:
+            _, ctx, okv, mask = hit
+            return x, t, ctx, M, okv, n_obj, mask
+        ctx = ctxs[0] if len(inputs) == 1 else torch.cat(ctxs, 0)
+        okv = None
+        if active:
+            per_input = []
+            for (kvs, Bo), b in zip(okv_lists, bs):
+                if Bo != b:
+                    kvs = [kv.view(1, n_obj, -1).expand(b, n_obj, kv.shape[-1]).reshape(b * n_obj, -1) for kv in kvs]
+                per_input.append(kvs)
+            okv = per_input[0] if len(inputs) == 1 else \
+                [torch.cat([l[i] for l in per_input], 0) for i in range(len(per_input[0]))]
         # instance-isolation mask words: inputs without a mask (the CFG null branch) get all-ones words
         mask = None
         if any(m is not None for m, _ in masks):
@@ -612,12 +636,10 @@ class UNetModel(PackedModule):
                     mqs.append(mq if mq.shape[0] == b else mq.expand(b, -1))
                     mks.append(mk if mk.shape[0] == b else mk.expand(b, -1))
             mask = (torch.cat(mqs, 0).contiguous(), torch.cat(mks, 0).contiguous())
-        if len(inputs) == 1:
-            return xs[0].contiguous(), ts[0].contiguous(), ctxs[0], M, (okv_lists[0] if active else None), n_obj, mask
-        x = torch.cat(xs, 0)
-        t = torch.cat(ts, 0)
-        ctx = torch.cat(ctxs, 0)
-        okv = [torch.cat([l[i] for l in okv_lists], 0) for i in range(len(okv_lists[0]))] if active else None
+        if len(self._cat_cache) >= 8:  # (an entry holds the concatenated text K/V: tens of MB to ~1 GB at MIS batch sizes)
+            self._cat_cache.clear()
+        keep = (ctxs, [k for k, _ in okv_lists], [m for m, _ in masks])  # keeps the keyed objects (and their ids) alive
+        self._cat_cache[key] = (keep, ctx, okv, mask)
         return x, t, ctx, M, okv, n_obj, mask
 
     @torch.no_grad()
@@ -687,12 +709,17 @@ class _CoreGraph:
     def replay(self, x, t, ctx, okv, mask=None):
         self.x.copy_(x)
         self.t.copy_(t)
-        self.ctx.copy_(ctx)
-        if self.okv is not None:
+        # step-invariant inputs: the static buffers already hold them when the very same (immutable, cached)
+        # tensor objects come back -- every step of a sampling run after the first
+        last = getattr(self, "_last", (None, None, None))
+        if ctx is not last[0]:
+            self.ctx.copy_(ctx)
+        if self.okv is not None and okv is not last[1]:
             for dst, src in zip(self.okv, okv):
                 dst.copy_(src)
-        if self.mask is not None:
+        if self.mask is not None and mask is not last[2]:
             self.mask[0].copy_(mask[0])
             self.mask[1].copy_(mask[1])
+        self._last = (ctx, okv, mask)  # (references keep the identities unique)
         self.graph.replay()
         return self.out.clone()

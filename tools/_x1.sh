@@ -1,4 +1,9 @@
 export PYTHONUNBUFFERED=1
-timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "gemm or conv" 2>&1 | tail -2
-timeout 300 python tools/plan_sweep.py 8 > gpurun_out/r2_plan_sweep_b8_new.log 2>&1; tail -1 gpurun_out/r2_plan_sweep_b8_new.log
-timeout 300 python tools/plan_sweep.py 16 > gpurun_out/r2_plan_sweep_b16_new.log 2>&1; awk '{print $1,$2,$3,$4,$5,$6,$7,$8}' gpurun_out/r2_plan_sweep_b16_new.log | column -t | cut -c1-100
+timeout 700 python -m pytest tests/test_parity_r2_gpu.py tests/test_modules_gpu.py tests/test_masked_gpu.py -m gpu -q -x 2>&1 | tail -3
+timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_x3.json 2> gpurun_out/r2_bench_x3.err
+python - <<'P'
+import json
+d=json.load(open('gpurun_out/r2_bench_x3.json'))
+print(d['value'], d['e2e']['value'], d['clocks'], d['mis036']['value'], d['mis036']['clocks'])
+P
+tail -3 gpurun_out/r2_bench_x3.err
