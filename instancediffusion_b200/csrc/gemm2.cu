@@ -38,11 +38,10 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 // Warpgroup 0 = {TMA, UMMA, 2 idle warps}; then EW epilogue warps (EW / 4 per TMEM lane quarter).
-// EW = 8 (two column halves) is the long-K configuration: the epilogue hides behind the next tile's
-// mainloop and the warps may use 224 registers.  EW = 16 (four column parts, 104 registers) is for the
-// short-K layers, which are bound by the epilogue's serial latency chain per 16-column chunk (TMEM load
-// -> wait -> table / residual LDS -> STS -> proxy fence -> TMA store, ~1000 clk): four epilogue warps per
-// scheduler instead of two hide it, and each warp owns half as many chunks per tile.
+// Only EW = 8 (two column halves, 224 registers per epilogue warp) is instantiated: EW = 12 and 16 (three /
+// four column parts, 152 / 104 registers) were built and measured slower for every shape of this UNet -- the
+// TMEM read path and, at 16, register spills cost more than the extra warps hide (profiles/README.md round 2).
+// The kernel keeps EW as a template parameter; the register split for the other values is left in place.
 constexpr int MAX_EPI_WARPS = 16;
 constexpr int CHUNK = 16;  // accumulator columns per tcgen05.ld
 constexpr int EPI_TAB_PB = 4;  // batches a conv tile may straddle and still use the smem epilogue table
