@@ -429,8 +429,7 @@ def main():
         # tensors (UniFusion tokens, object / text K/V): nothing is carried over between timed steps
         model.undo_first_conv_restore()
         set_alpha_scale(model, 1)
-        model._ctx_cache.clear()
-        model._obj_cache.clear()
+        model.clear_hoisted()
 
     def measure(mis, steps, warmup):
         """One leg: `warmup` untimed + `steps` timed sample() calls with inputs resident in HBM, then `steps`

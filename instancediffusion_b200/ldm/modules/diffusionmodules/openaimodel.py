@@ -463,6 +463,7 @@ class UNetModel(PackedModule):
         kv = ops.gemm(c16, p["w_ctx_all"])
         if len(self._ctx_cache) > 64:
             self._ctx_cache.clear()
+            self._cat_cache.clear()
         self._ctx_cache[key] = (context, kv)  # keep `context` alive so the key stays unique
         return kv
 
@@ -491,14 +492,20 @@ class UNetModel(PackedModule):
         mask = attention_mask_words(blocks[0].fuser, gi, drop_box_mask, Bo, 64 * 64, n_obj)
         if len(self._obj_cache) > 64:
             self._obj_cache.clear()
+            self._cat_cache.clear()
         val = (kvs, Bo, n_obj, mask)
         self._obj_cache[key] = (gi, val)
         return val
 
-    def clear_caches(self):
+    def clear_hoisted(self):
+        """Drop the per-sample hoisted tensors (text K/V, UniFusion tokens / object K/V, their concatenations);
+        captured graphs stay.  What a server calls between requests."""
         self._ctx_cache.clear()
         self._obj_cache.clear()
         self._cat_cache.clear()
+
+    def clear_caches(self):
+        self.clear_hoisted()
         self._graphs.clear()
 
     # ------------------------------------------------------------------------------------------
@@ -636,7 +643,7 @@ class UNetModel(PackedModule):
                     mqs.append(mq if mq.shape[0] == b else mq.expand(b, -1))
                     mks.append(mk if mk.shape[0] == b else mk.expand(b, -1))
             mask = (torch.cat(mqs, 0).contiguous(), torch.cat(mks, 0).contiguous())
-        if len(self._cat_cache) >= 8:  # (an entry holds the concatenated text K/V: tens of MB to ~1 GB at MIS batch sizes)
+        if len(self._cat_cache) >= 6:  # (an entry holds the concatenated text K/V: tens of MB to ~1 GB at MIS batch sizes)
             self._cat_cache.clear()
         keep = (ctxs, [k for k, _ in okv_lists], [m for m, _ in masks])  # keeps the keyed objects (and their ids) alive
         self._cat_cache[key] = (keep, ctx, okv, mask)

@@ -17,7 +17,7 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us":
 def short(name):
     m = re.search(r"(\w+_kernel)(<[^>]*>)?", name)
     if m and ("idiff" in name or m.group(1).split("_kernel")[0] in (
-            "gemm2", "gemm", "attention2", "attention", "gn_stats", "gn_apply", "layernorm40", "layernorm_generic",
+            "gemm2", "gemm", "attention2", "attention", "gn_stats", "gn_apply", "gn_fused", "row_stats", "layernorm40", "layernorm_generic",
             "scaleu_coef", "scaleu_reduce", "scaleu_apply", "upsample2x", "im2col_s2", "silu_f16", "fourier_embed",
             "timestep_embedding", "plms_update", "latent_mean", "nchw_f32_to_nhwc_f16", "nhwc_f16_to_nchw_f32")):
         return m.group(1) + (m.group(2) or "")

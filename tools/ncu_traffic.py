@@ -15,7 +15,7 @@ seen = collections.defaultdict(set)
 unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
 for r in csv.DictReader(lines):
     name = r["Kernel Name"]
-    m = re.search(r"(gemm2_kernel|attention2_kernel|attention_kernel|gn_stats_kernel|gn_apply_kernel|layernorm\w*|scaleu_\w+)", name)
+    m = re.search(r"(gemm2_kernel|attention2_kernel|attention_kernel|gn_stats_kernel|gn_apply_kernel|gn_fused_kernel|layernorm\w*|scaleu_\w+)", name)
     key = m.group(1) if m else "other"
     if key.startswith("layernorm"):
         key = "layernorm_kernel"
