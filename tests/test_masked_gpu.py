@@ -116,7 +116,7 @@ def test_masked_gated_block_matches_reference_golden(cuda_device, name):
         got = got[:, ::spec["stride"]].float().cpu()
         rel = ((got - gold[key]).norm() / gold[key].norm()).item()
         print(f"[{key}] rel_l2={rel:.3e}")
-        assert torch.isfinite(got).all() and rel < 3e-3, (key, rel)
+        assert torch.isfinite(got).all() and rel < 8e-4, (key, rel)  # <= 2x measured (3.7-3.9e-4)
 
 
 def test_unet_with_attention_mask_batched_equals_single(cuda_device):

@@ -48,7 +48,7 @@ def test_module_matches_reference_golden(cuda_device, name):
     spec = cases.MODULE_CASES[name]
     out = cases.run_module_case(name, spec, _mirror_class(spec["module"]), device=cuda_device)
     # fp16 operands / fp32 accumulation through <= ~12 chained GEMMs: 3e-3 relative L2
-    _report(out, gold[name], name, 3e-3, 1e-2)
+    _report(out, gold[name], name, 1.4e-3, 2.1e-3)  # <= 2x measured (max over the cases: 7.0e-4 / 1.07e-3)
 
 
 def test_fourier_filter_matches_reference_golden(cuda_device):
@@ -57,10 +57,10 @@ def test_fourier_filter_matches_reference_golden(cuda_device):
     for name, spec in cases.FOURIER_CASES.items():
         x = (cases.synth_input(name, "x", spec["shape"]) + 0.5).to(cuda_device)
         out = Fourier_filter(x, threshold=1, scale=spec["scale"])
-        _report(out, gold[name], name, 1e-3, 2e-3)  # fp16 in/out of an fp32 closed form
+        _report(out, gold[name], name, 6e-4, 1.2e-3)  # fp16 in/out of an fp32 closed form; measured 3.1e-4 / 6.3e-4
     from instancediffusion_b200 import ops
     t = torch.tensor([981.0, 1.0, 501.0, 21.0], device=cuda_device)
-    _report(ops.timestep_embedding(t, 320), gold["timestep_embedding"], "timestep_embedding", 1e-3, 2e-3)
+    _report(ops.timestep_embedding(t, 320), gold["timestep_embedding"], "timestep_embedding", 3e-4, 5e-4)  # measured 1.5e-4 / 2.4e-4
 
 
 @pytest.mark.parametrize("name", list(cases.UNIFUSION_CASES))
@@ -79,7 +79,7 @@ def test_unifusion_matches_reference_golden(cuda_device, name):
     gi = GroundingNetInput().prepare(gb)
     objs, dbm = net(gi["boxes"], gi["masks"], gi["positive_embeddings"], gi["scribbles"], gi["polygons"],
                     gi["segs"], gi["points"])
-    _report(objs, gold[name], name, 3e-3, 1e-2)
+    _report(objs, gold[name], name, 1.1e-3, 1.2e-3)  # measured 5.6e-4 / 6.0e-4
     assert int(dbm) == int(gold[name + "/drop_box_mask"])
 
 
@@ -97,7 +97,7 @@ def test_convnext_matches_reference_golden(cuda_device, name):
     with torch.no_grad():
         out = m(x)
     # a Block is 2 GEMMs deep (3e-3 like the other modules); the trunk chains 18 blocks + 4 strided convs
-    _report(out, gold[name], name, 3e-3 if "block" in name else 6e-3, 2e-2)
+    _report(out, gold[name], name, 6e-4 if "block" in name else 2.3e-3, 1.4e-3 if "block" in name else 2.2e-3)  # measured 3.0e-4 / 7.1e-4 (blocks), 1.16e-3 / 1.11e-3 (whole encoder)
 
 
 @pytest.mark.parametrize("name", list(cases.UNIFUSION_MASK_CASES))
@@ -121,10 +121,10 @@ def test_unifusion_mask_matches_reference_golden(cuda_device, name):
         gi["segs"].float(), net.pk()["w_inconv"], net.pk()["b_inconv"], 512)
     feat, fh, fw = net.convnext_tiny_backbone._features(y, spec["batch"], 512, 512)
     ref_feat = gold[name + "/convnext_feat"]
-    _report(feat.view(spec["batch"], fh, fw, -1).permute(0, 3, 1, 2), ref_feat, name + "/convnext_feat", 6e-3, 3e-2)
+    _report(feat.view(spec["batch"], fh, fw, -1).permute(0, 3, 1, 2), ref_feat, name + "/convnext_feat", 2.4e-3, 3e-3)  # measured 1.21e-3 / 1.50e-3
     objs, dbm = net(gi["boxes"], gi["masks"], gi["positive_embeddings"], gi["scribbles"], gi["polygons"],
                     gi["segs"], gi["points"])
-    _report(objs, gold[name], name, 4e-3, 2e-2)
+    _report(objs, gold[name], name, 1.8e-3, 2.4e-3)  # measured 9.1e-4 / 1.21e-3
     assert int(dbm) == int(gold[name + "/drop_box_mask"])
 
 
@@ -158,30 +158,30 @@ def test_unet_eps_matches_reference_golden(cuda_device, unet):
     set_alpha_scale(unet, 1)
     objs, _ = unet.position_net(gi["boxes"], gi["masks"], gi["positive_embeddings"], gi["scribbles"], gi["polygons"],
                                 gi["segs"], gi["points"])
-    _report(objs, gold["objs"], "unet/objs", 3e-3, 1e-2)
+    _report(objs, gold["objs"], "unet/objs", 1.1e-3, 1.2e-3)
     # one full denoise forward: ~200 fp16 layers deep.  Measured 2.0e-3 relative L2;
     # the bound is 2x that.  (The reference itself under autocast(fp16) deviates as much:
     # tests/test_parity_r2_gpu.py::test_fp16_envelope_eps_and_latents.)
     for graph in (False, True):
         unet.use_cuda_graph = graph
         eps_c = unet(dict(x=inp["x"], timesteps=ts, context=inp["context"], grounding_input=gi))
-        _report(eps_c, gold["eps_cond"], f"unet/eps_cond graph={graph}", 4e-3, 2e-2)
+        _report(eps_c, gold["eps_cond"], f"unet/eps_cond graph={graph}", 4e-3, 4.5e-3)
         eps_u = unet(dict(x=inp["x"], timesteps=ts, context=uc))
-        _report(eps_u, gold["eps_null"], f"unet/eps_null graph={graph}", 4e-3, 2e-2)
+        _report(eps_u, gold["eps_null"], f"unet/eps_null graph={graph}", 4e-3, 4.5e-3)
     # batched cond+uncond: every row against the *reference golden* (not against our own single path), same
     # bound.  Tile widths / stream-K splits depend on M, so batched and single runs round differently at the
     # fp16 level and are not bit-equal; both must sit inside the same distance of the fp32 reference.
     both = unet.forward_batched([dict(x=inp["x"], timesteps=ts, context=inp["context"], grounding_input=gi),
                                  dict(x=inp["x"], timesteps=ts, context=uc)])
-    _report(both[0], gold["eps_cond"], "batched cond vs golden", 4e-3, 2e-2)
-    _report(both[1], gold["eps_null"], "batched uncond vs golden", 4e-3, 2e-2)
-    _report(both[0], eps_c.cpu(), "batched cond vs single", 4e-3, 2e-2)
-    _report(both[1], eps_u.cpu(), "batched uncond vs single", 4e-3, 2e-2)
+    _report(both[0], gold["eps_cond"], "batched cond vs golden", 4e-3, 4.5e-3)
+    _report(both[1], gold["eps_null"], "batched uncond vs golden", 4e-3, 4.5e-3)
+    _report(both[0], eps_c.cpu(), "batched cond vs single", 3.4e-3, 3.5e-3)  # measured 1.6-1.7e-3: two fp16 roundings of the same eps
+    _report(both[1], eps_u.cpu(), "batched uncond vs single", 3.4e-3, 3.5e-3)
     # alpha = 0: fusers off + SD1.5 first conv (openaimodel.py:469-480)
     set_alpha_scale(unet, 0)
     unet.set_sd_first_conv(unet._sd_conv)
     eps_0 = unet(dict(x=inp["x"], timesteps=ts, context=inp["context"], grounding_input=gi))
-    _report(eps_0, gold["eps_alpha0"], "unet/eps_alpha0", 4e-3, 2e-2)
+    _report(eps_0, gold["eps_alpha0"], "unet/eps_alpha0", 4e-3, 4.5e-3)
     unet.undo_first_conv_restore()
     set_alpha_scale(unet, 1)
 
@@ -224,4 +224,4 @@ def test_sampler_latent_vs_reference_golden(cuda_device, unet, name):
         unet.restore_first_conv_from_SD = orig
         unet.undo_first_conv_restore()
         set_alpha_scale(unet, 1)
-    _report(x, gold[name], f"sampler/{name}", 7.4e-3, 5e-2)  # <= 2x measured: 2.8e-3 (MIS S=10) / 3.7e-3 (PLMS S=4)
+    _report(x, gold[name], f"sampler/{name}", 7.2e-3, 8.7e-3)  # <= 2x measured: 2.8e-3 (MIS S=10) / 3.7e-3 (PLMS S=4)

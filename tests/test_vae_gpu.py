@@ -53,7 +53,7 @@ def test_vae_decode_matches_reference_golden(cuda_device, vae, name):
     img = vae.decode(z)
     rel, mx = _rel(img, gold[name])
     print(f"[vae/{name}] rel_l2={rel:.3e} max_err/ref_max={mx:.3e}")
-    assert rel < 6e-3 and mx < 3e-2, (name, rel, mx)
+    assert rel < 2.5e-3 and mx < 3e-3, (name, rel, mx)  # <= 2x measured: 1.25e-3 / 1.49e-3
 
 
 def test_vae_encoder_moments_match_reference_golden(cuda_device, vae):
@@ -65,7 +65,7 @@ def test_vae_encoder_moments_match_reference_golden(cuda_device, vae):
     mom = torch.nn.functional.conv2d(h, vae.quant_conv.weight.float(), vae.quant_conv.bias.float())
     rel, mx = _rel(mom, gold["encode_64"])
     print(f"[vae/encode_64] rel_l2={rel:.3e} max_err/ref_max={mx:.3e}")
-    assert rel < 6e-3 and mx < 3e-2, (rel, mx)
+    assert rel < 3.3e-3 and mx < 3e-3, (rel, mx)  # <= 2x measured (encode moments 1.66e-3 / 1.50e-3)
 
 
 def test_vae_decode_512_image_vs_fp32_oracle(cuda_device, vae):
@@ -85,7 +85,7 @@ def test_vae_decode_512_image_vs_fp32_oracle(cuda_device, vae):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
     rel, mx = _rel(img, ref)
     print(f"[vae/decode_512] rel_l2={rel:.3e} max_err/ref_max={mx:.3e}")
-    assert rel < 6e-3 and mx < 3e-2, (rel, mx)
+    assert rel < 2.5e-3 and mx < 3e-3, (rel, mx)  # <= 2x measured: 1.23e-3 / 1.49e-3
 
 
 def test_softmax_rows_and_latent_prologue(cuda_device):
