@@ -268,6 +268,25 @@ int idiff_vae_latent_in(const float* z, const float* w, const float* bias, float
    the attention weights of AttnBlock (model.py:185-187); the 1/sqrt(c) scale is folded into the q projection */
 int idiff_softmax_rows(void* x, int rows, int n, long ld, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * CLIP text encoder (host prep): the per-phrase pooled feature of
+ * utils/model.py:130-152 (get_clip_feature -> text_model pooler_output) and the prompt context of
+ * ldm/modules/encoders/modules.py:144-172 (FrozenCLIPEmbedder -> last_hidden_state); both are Hugging Face
+ * CLIPTextModel (transformers 4.27, requirements.txt:247).  Its linear layers are idiff_gemm calls (QuickGELU =
+ * SiLU epilogue on weights pre-scaled by 1.702), its LayerNorms idiff_layernorm; these are the rest.
+ * ------------------------------------------------------------------------------------------- */
+/* out[r] = tok_table[ids[r]] + pos_table[r % tokens_per_seq]; ids int64 [rows] (clamped to the table), tables and
+   out in the 16-bit storage type, [*, channels] row-major, channels % 8 == 0 */
+int idiff_embed_tokens(const long long* ids, const void* tok_table, const void* pos_table, void* out, int rows,
+                       int tokens_per_seq, int vocab, int channels, void* stream);
+/* out = softmax(q k^T scale + causal mask) v per (sequence, head) for sequences of <= 128 tokens, head_dim 64.
+   q / k / v: 16-bit [batch*tokens, >= heads*head_dim] with the common row stride ld_qkv (the fused QKV GEMM output);
+   out [batch*tokens, heads*head_dim], row stride ld_out.  key_len (optional, int32 [batch]): keys at positions
+   >= key_len[b] are padding and masked in addition to the causal mask. */
+int idiff_causal_attention_small(const void* q, const void* k, const void* v, void* out, const int* key_len,
+                                 int ld_qkv, int ld_out, int batch, int tokens, int heads, int head_dim, float scale,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

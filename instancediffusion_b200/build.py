@@ -14,7 +14,7 @@ import sys
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libidiff_b200.so")
 LIB_BF16 = os.path.join(CSRC, "libidiff_b200_bf16.so")  # same sources, -DIDIFF_STORAGE_BF16=1 (include/idiff_b200.h)
-SOURCES = ["host.cu", "gemm2.cu", "attention.cu", "attention2.cu", "norm.cu", "scaleu.cu", "elementwise.cu", "convnext.cu", "vae.cu"]
+SOURCES = ["host.cu", "gemm2.cu", "attention.cu", "attention2.cu", "norm.cu", "scaleu.cu", "elementwise.cu", "convnext.cu", "vae.cu", "clip.cu"]
 HEADERS = ["common.cuh", "host.cuh", os.path.join("..", "..", "include", "idiff_b200.h")]
 
 NVCC_FLAGS = [

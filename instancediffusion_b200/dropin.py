@@ -11,6 +11,7 @@ SURVEY.md section 8b resolve to this package's mirrors:
     utils.model  (set_alpha_scale / alpha_generator only; everything else stays the reference's)
     ldm.models.autoencoder, ldm.modules.diffusionmodules.model   (first stage: AutoencoderKL.decode right
         after the sampler loop, inference.py:96; `install(first_stage=False)` leaves it to the reference)
+    ldm.modules.encoders.modules   (only with `install(text_encoder=True)`: FrozenCLIPEmbedder, configs/*.yaml:72)
 
 With a reference checkout on sys.path (or passed as `reference_root` / $IDIFF_REF) the *parent*
 packages stay the reference's own (`ldm`, `ldm.modules`, `ldm.models`, `utils` are namespace
@@ -46,6 +47,11 @@ _MAP = {
 _FIRST_STAGE = {
     "ldm.models.autoencoder": "instancediffusion_b200.ldm.models.autoencoder",
     "ldm.modules.diffusionmodules.model": "instancediffusion_b200.ldm.modules.diffusionmodules.model",
+}
+# opt-in (install(text_encoder=True)): the CLIP text tower of FrozenCLIPEmbedder on the B200 kernels; the other
+# encoder classes of that file (BERT, FrozenCLIPTextEmbedder, ...) are fetched lazily from the reference's own file
+_TEXT_ENCODER = {
+    "ldm.modules.encoders.modules": "instancediffusion_b200.ldm.modules.encoders.modules",
 }
 _PKGS = {
     "ldm": "instancediffusion_b200.ldm",
@@ -114,12 +120,12 @@ def _bind(alias: str, module: types.ModuleType) -> None:
 
 
 def install(shadow_utils_model: bool = True, reference_root: Optional[str] = None,
-            first_stage: bool = True) -> Optional[str]:
+            first_stage: bool = True, text_encoder: bool = False) -> Optional[str]:
     """Alias the mirror leaf modules under the reference's import paths; returns the reference root
     that keeps serving the non-mirrored modules (None if no checkout is visible)."""
     root = find_reference_root(reference_root)
     from .utils import model as um
-    leaf_map = {**_MAP, **(_FIRST_STAGE if first_stage else {})}
+    leaf_map = {**_MAP, **(_FIRST_STAGE if first_stage else {}), **(_TEXT_ENCODER if text_encoder else {})}
     if root is not None:
         if root not in sys.path:
             sys.path.insert(0, root)
@@ -159,7 +165,10 @@ def install(shadow_utils_model: bool = True, reference_root: Optional[str] = Non
                 _bind("utils.model", shim)
         return root
     # no checkout: the mirrors' packages stand in as parents
-    for alias, real in {**_PKGS, **leaf_map}.items():
+    pkgs = dict(_PKGS)
+    if text_encoder:
+        pkgs["ldm.modules.encoders"] = "instancediffusion_b200.ldm.modules.encoders"
+    for alias, real in {**pkgs, **leaf_map}.items():
         sys.modules[alias] = importlib.import_module(real)
         _installed.append(alias)
     if shadow_utils_model:

@@ -562,6 +562,47 @@ def softmax_rows_(x: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# CLIP text encoder pieces (csrc/clip.cu)
+# ------------------------------------------------------------------------------------------------
+def embed_tokens(ids: torch.Tensor, tok_table: torch.Tensor, pos_table: torch.Tensor) -> torch.Tensor:
+    """ids int64 (B, T); tok_table 16-bit [V, C]; pos_table 16-bit [>= T, C] -> 16-bit [B*T, C] = tok[ids] + pos[t]."""
+    lib = _lib.load()
+    _req(ids, torch.int64, "ids")
+    _req(tok_table, HALF, "tok_table")
+    _req(pos_table, HALF, "pos_table")
+    B, T = ids.shape
+    V, Cc = tok_table.shape
+    if pos_table.shape[0] < T or pos_table.shape[1] != Cc or not (tok_table.is_contiguous() and pos_table.is_contiguous()):
+        raise _lib.IdiffError(f"embed_tokens: position table {tuple(pos_table.shape)} does not cover {T} tokens of width {Cc}")
+    ids = ids.contiguous()
+    out = torch.empty((B * T, Cc), dtype=HALF, device=ids.device)
+    check(lib.idiff_embed_tokens(ids.data_ptr(), tok_table.data_ptr(), pos_table.data_ptr(), out.data_ptr(), B * T, T, V, Cc,
+                                 _stream()), "idiff_embed_tokens")
+    return out
+
+
+def causal_attention_small(qkv: torch.Tensor, *, batch: int, tokens: int, heads: int, head_dim: int, scale: float,
+                           key_len: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv 16-bit [batch*tokens, 3*heads*head_dim] (q | k | v) -> 16-bit [batch*tokens, heads*head_dim]: causal
+    softmax attention for short sequences (CLIP text: 77 tokens, 12 heads of 64)."""
+    lib = _lib.load()
+    _req(qkv, HALF, "qkv")
+    C_ = heads * head_dim
+    if qkv.dim() != 2 or qkv.shape[0] != batch * tokens or qkv.shape[1] < 3 * C_:
+        raise _lib.IdiffError(f"causal_attention_small: qkv {tuple(qkv.shape)} vs batch {batch} tokens {tokens} width {3 * C_}")
+    if key_len is not None:
+        _req(key_len, torch.int32, "key_len")
+        if key_len.numel() != batch:
+            raise _lib.IdiffError("causal_attention_small: key_len must hold one length per sequence")
+    out = torch.empty((batch * tokens, C_), dtype=HALF, device=qkv.device)
+    flops = 2.0 * batch * heads * tokens * tokens * head_dim  # (causal: half of 4 N^2 d)
+    check(_launch("attention_causal_small", flops, 2.0 * (qkv.numel() + out.numel()), lambda: lib.idiff_causal_attention_small(
+        qkv.data_ptr(), qkv[:, C_:].data_ptr(), qkv[:, 2 * C_:].data_ptr(), out.data_ptr(), _ptr(key_len), qkv.stride(0),
+        out.stride(0), batch, tokens, heads, head_dim, float(scale), _stream())), "idiff_causal_attention_small")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # instance-isolation attention mask (utils/input.py:34-37, attention.py:203-247)
 # ------------------------------------------------------------------------------------------------
 def boxes_to_attmask(boxes: torch.Tensor, counts: torch.Tensor, size: int = 64) -> torch.Tensor:

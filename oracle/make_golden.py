@@ -278,6 +278,29 @@ def gen_vae(ref):
     torch.save(out, os.path.join(GOLDEN, "vae.pt"))
 
 
+def gen_clip():
+    """CLIP text tower (tests/golden/clip_text.pt): the installed transformers CLIPTextModel -- the third-party model the
+    reference calls (encoders/modules.py:147-165, utils/model.py:146-151) -- at full size with the synthetic weights,
+    on seeded token ids; last_hidden_state and pooler_output."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+    from instancediffusion_b200.weights import synth_tensor
+    cfg = CLIPTextConfig(hidden_act="quick_gelu", eos_token_id=cases.CLIP_EOS, bos_token_id=cases.CLIP_BOS, pad_token_id=cases.CLIP_EOS,
+                         **torch_oracle.CLIP_TEXT_CONFIG)
+    with ref_harness.fast_init():
+        m = CLIPTextModel(cfg).eval()
+    m.load_state_dict({k: synth_tensor("clip." + k, tuple(v.shape), cases.WEIGHT_SEED) for k, v in m.state_dict().items()}, strict=True)
+    out = {}
+    with torch.no_grad():
+        for name, spec in cases.CLIP_CASES.items():
+            ids = cases.clip_token_ids(spec)
+            t = time.time()
+            o = m(input_ids=ids)
+            out[name + "/last_hidden_state"] = o.last_hidden_state.float().contiguous()
+            out[name + "/pooler_output"] = o.pooler_output.float().contiguous()
+            print(f"  clip {name}: {time.time() - t:.1f}s last {tuple(o.last_hidden_state.shape)} absmax={o.last_hidden_state.abs().max():.3f}")
+    torch.save(out, os.path.join(GOLDEN, "clip_text.pt"))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--threads", type=int, default=os.cpu_count())
@@ -286,6 +309,10 @@ def main():
     only = set(args.only.split(","))
     torch.set_num_threads(args.threads)
     os.makedirs(GOLDEN, exist_ok=True)
+    if "clip" in only:
+        print("clip text tower"); gen_clip()
+        if only == {"clip"}:
+            return
     ref = ref_harness.import_reference()
     print(f"reference at {ref.root}; torch {torch.__version__}; threads {torch.get_num_threads()}")
     if "modules" in only:

@@ -495,3 +495,47 @@ def vae_encode_moments(sd: SD, x, cfg: dict = VAE_DDCONFIG):
     h = vae_resnet_block(sd, e + ".mid.block_2", h)
     h = F.conv2d(F.silu(_gn6(sd, e + ".norm_out", h)), sd[e + ".conv_out.weight"], sd[e + ".conv_out.bias"], padding=1)
     return F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])
+
+
+# ------------------------------------------------------------------------------------------------
+# CLIP text encoder.  Third-party arithmetic: Hugging Face transformers' CLIPTextModel,
+# pinned transformers==4.27.0 by the reference (requirements.txt:247), called at ldm/modules/encoders/modules.py:
+# 147-165 (FrozenCLIPEmbedder) and utils/model.py:146-151 (get_clip_feature).  Published algorithm
+# (modeling_clip.py: CLIPTextEmbeddings, CLIPEncoderLayer, CLIPAttention, CLIPMLP with quick_gelu,
+# CLIPTextTransformer), restated over the model's own state_dict; pinned by tests/golden/clip_text.pt, produced by
+# the installed transformers CLIPTextModel itself (oracle/make_golden.py --only clip).
+# ------------------------------------------------------------------------------------------------
+CLIP_TEXT_CONFIG = dict(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                        num_attention_heads=12, max_position_embeddings=77)
+
+
+def clip_text_forward(sd: SD, input_ids: torch.Tensor, heads: int = 12, eps: float = 1e-5, prefix: str = "text_model",
+                      key_len: Optional[torch.Tensor] = None):
+    """-> (last_hidden_state (B, T, C), pooler_output (B, C)).  Pre-LN transformer, causal mask (plus key padding when
+    key_len is given), QuickGELU x * sigmoid(1.702 x), final LayerNorm, pooled = state at the highest token id (EOS)."""
+    B, T = input_ids.shape
+    x = sd[f"{prefix}.embeddings.token_embedding.weight"][input_ids] + sd[f"{prefix}.embeddings.position_embedding.weight"][:T][None]
+    C = x.shape[-1]
+    d = C // heads
+    mask = torch.full((T, T), float("-inf"), device=x.device).triu(1)[None, None]  # key j visible to query i iff j <= i
+    if key_len is not None:
+        pad = torch.arange(T, device=x.device)[None, :] >= key_len.to(x.device)[:, None]
+        mask = mask + torch.zeros((B, 1, T, T), device=x.device).masked_fill(pad[:, None, None, :], float("-inf"))
+    n_layers = 1 + max(int(k.split(".")[3]) for k in sd if k.startswith(f"{prefix}.encoder.layers."))
+    for i in range(n_layers):
+        L = f"{prefix}.encoder.layers.{i}"
+        h = F.layer_norm(x, (C,), sd[L + ".layer_norm1.weight"], sd[L + ".layer_norm1.bias"], eps)
+        q = F.linear(h, sd[L + ".self_attn.q_proj.weight"], sd[L + ".self_attn.q_proj.bias"]) * d ** -0.5
+        k = F.linear(h, sd[L + ".self_attn.k_proj.weight"], sd[L + ".self_attn.k_proj.bias"])
+        v = F.linear(h, sd[L + ".self_attn.v_proj.weight"], sd[L + ".self_attn.v_proj.bias"])
+        sp = lambda t: t.view(B, T, heads, d).transpose(1, 2)
+        a = torch.softmax(sp(q) @ sp(k).transpose(-1, -2) + mask, dim=-1) @ sp(v)
+        a = a.transpose(1, 2).reshape(B, T, C)
+        x = x + F.linear(a, sd[L + ".self_attn.out_proj.weight"], sd[L + ".self_attn.out_proj.bias"])
+        h = F.layer_norm(x, (C,), sd[L + ".layer_norm2.weight"], sd[L + ".layer_norm2.bias"], eps)
+        u = F.linear(h, sd[L + ".mlp.fc1.weight"], sd[L + ".mlp.fc1.bias"])
+        x = x + F.linear(u * torch.sigmoid(1.702 * u), sd[L + ".mlp.fc2.weight"], sd[L + ".mlp.fc2.bias"])
+    last = F.layer_norm(x, (C,), sd[f"{prefix}.final_layer_norm.weight"], sd[f"{prefix}.final_layer_norm.bias"], eps)
+    pooled = last[torch.arange(B, device=x.device), input_ids.argmax(dim=-1)]
+    return last, pooled
+

@@ -144,6 +144,23 @@ VAE_CASES = {
 }
 
 
+# CLIP text encoder (host prep): full-size text tower, synthetic weights, seeded token ids laid out
+# like the tokenizer's output: BOS, `n` word tokens, EOS, then EOS padding (openai/clip pads with <|endoftext|>)
+CLIP_CASES = {
+    "clip_b3": dict(lengths=(5, 20, 75), seed=71),
+}
+CLIP_BOS, CLIP_EOS = 49406, 49407
+
+
+def clip_token_ids(spec: dict) -> torch.Tensor:
+    g = torch.Generator().manual_seed(spec["seed"])
+    rows = []
+    for n in spec["lengths"]:
+        words = torch.randint(0, CLIP_BOS, (n,), generator=g)
+        rows.append(torch.cat([torch.tensor([CLIP_BOS]), words, torch.full((77 - 1 - n,), CLIP_EOS)]))
+    return torch.stack(rows).long()
+
+
 def build_inputs(name: str, spec: dict) -> Dict[str, torch.Tensor]:
     ins = {k: synth_input(name, k, shp) for k, shp in spec["inputs"].items()}
     if spec.get("same_kv"):

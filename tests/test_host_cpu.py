@@ -190,6 +190,25 @@ def test_dropin_install_resolves_reference_paths():
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 
+def test_dropin_text_encoder_opt_in():
+    """install(text_encoder=True): configs/*.yaml:72 `ldm.modules.encoders.modules.FrozenCLIPEmbedder` resolves to the
+    mirror (CLIP text tower on the B200 kernels), with HF's parameter names under `transformer.`; without the flag the
+    path stays the reference's."""
+    import subprocess
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from instancediffusion_b200 import dropin; dropin.install(text_encoder=True)\n"
+        "from ldm.util import get_obj_from_str\n"
+        "cls = get_obj_from_str('ldm.modules.encoders.modules.FrozenCLIPEmbedder')\n"
+        "assert cls.__module__.startswith('instancediffusion_b200.'), cls.__module__\n"
+        "enc = cls(device='cpu')\n"
+        "keys = list(enc.state_dict())\n"
+        "assert len(keys) == 196 and keys[0] == 'transformer.text_model.embeddings.token_embedding.weight', keys[:2]\n"
+        "print('ok')\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
 def test_dropin_keeps_reference_packages_as_parents():
     """With the reference checkout on sys.path, install() must shadow only the hot-path leaf modules:
     the reference's inference.py import block (:14-22) and every `target:` of configs/test_box.yaml

@@ -275,3 +275,45 @@ def test_masked_gated_attention_restatement_matches_reference(name):
         free = TO.gated_self_attention(sd, "m", x, objs)
     _close(got[:, ::spec["stride"]], gold[name], 1e-4, 2e-5, name)
     _close(free[:, ::spec["stride"]], gold[name + "/free"], 1e-4, 2e-5, name + "/free")
+
+
+# ------------------------------------------------------------------------------------------------
+# CLIP text tower (third-party: transformers CLIPTextModel; host prep)
+# ------------------------------------------------------------------------------------------------
+def _clip_sd():
+    from instancediffusion_b200.ldm.modules.encoders.modules import CLIPTextModel
+    from instancediffusion_b200.weights import synth_tensor
+    with torch.device("meta"):
+        m = CLIPTextModel()
+    return {k: synth_tensor("clip." + k, tuple(v.shape), cases.WEIGHT_SEED) for k, v in m.state_dict().items()}
+
+
+@pytest.mark.parametrize("name", list(cases.CLIP_CASES))
+def test_clip_text_restatement_matches_transformers(name):
+    """oracle clip_text_forward vs the golden produced by the installed transformers CLIPTextModel with the same
+    synthetic weights (tests/golden/clip_text.pt); the mirror's state_dict keys are HF's, so the same dict feeds both."""
+    gold = _load("clip_text.pt")
+    ids = cases.clip_token_ids(cases.CLIP_CASES[name])
+    with torch.no_grad():
+        last, pooled = TO.clip_text_forward(_clip_sd(), ids)
+    _close(last, gold[name + "/last_hidden_state"], 1e-4, 5e-5, f"clip {name} last_hidden_state")
+    _close(pooled, gold[name + "/pooler_output"], 1e-4, 5e-5, f"clip {name} pooler_output")
+
+
+def test_clip_text_key_padding_mask_matches_transformers():
+    """get_clip_feature (utils/model.py:146-151) passes the processor's attention_mask: the restated key-padding mask
+    against transformers on a padded batch (tiny random model built here: no fixture needed)."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+    torch.manual_seed(3)
+    cfg = CLIPTextConfig(vocab_size=100, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                         max_position_embeddings=16, hidden_act="quick_gelu", eos_token_id=99, bos_token_id=98, pad_token_id=0)
+    m = CLIPTextModel(cfg).eval()
+    ids = torch.tensor([[98, 5, 6, 99, 0, 0, 0, 0], [98, 7, 8, 9, 10, 11, 12, 99]])
+    am = (torch.arange(8)[None] < torch.tensor([4, 8])[:, None]).long()
+    with torch.no_grad():
+        ref = m(input_ids=ids, attention_mask=am)
+        last, pooled = TO.clip_text_forward(m.state_dict(), ids, heads=4, key_len=am.sum(-1))
+    # rows of the padding region depend on the (implementation-defined) treatment of fully masked queries: compare real tokens
+    for b, n in enumerate((4, 8)):
+        _close(last[b, :n], ref.last_hidden_state[b, :n], 1e-4, 5e-5, f"clip padded batch row {b}")
+    _close(pooled, ref.pooler_output, 1e-4, 5e-5, "clip padded batch pooled")
