@@ -297,6 +297,17 @@ def _worker(rank, world, port, q):
     dist.all_gather(gathered, flat)
     same = all(torch.equal(gathered[0], g) for g in gathered)
     mx = parallel.max_over_ranks(float(rank + 1), "cpu")
+    # pre-packed checkpoint route (utils/checkpoint.py): rank 0 packs, the others receive into empty buffers
+    from instancediffusion_b200.utils import checkpoint as ck
+    torch.manual_seed(200 + rank)
+    m2 = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.LayerNorm(32))
+    pack = ck.pack_state_dict(m2.state_dict()) if rank == 0 else ck.empty_like_pack(m2, "cpu")
+    sent_pack = ck.broadcast_pack(pack, src=0)
+    ck.unpack_into(m2, pack)
+    flat2 = torch.cat([p.reshape(-1) for p in m2.parameters()])
+    g2 = [torch.zeros_like(flat2) for _ in range(w)]
+    dist.all_gather(g2, flat2)
+    same = same and all(torch.equal(g2[0], g) for g in g2) and sent_pack == ck.pack_bytes(pack) == 16 * 32 * 2 + 3 * 32 * 4
     q.put((rank, same, sent, parallel.shard_indices(7, r, w), mx))
     parallel.barrier()
     dist.destroy_process_group()
