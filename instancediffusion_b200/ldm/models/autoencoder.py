@@ -10,7 +10,6 @@ GroupNorm kernels of the UNet (ldm/modules/diffusionmodules/model.py in this pac
 from __future__ import annotations
 
 import torch
-import torch.nn as nn
 
 from ... import ops
 from ..modules._base import PackedModule, f32

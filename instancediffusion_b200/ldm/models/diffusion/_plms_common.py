@@ -9,7 +9,7 @@ B200-first restructuring of `p_sample_plms` (plms.py:117-167 == plms_instance.py
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List
 
 import numpy as np
 import torch

@@ -16,14 +16,13 @@ parameters live in the parent block (attention.py:294-295, 320-322).
 from __future__ import annotations
 
 import math
-from typing import Optional
 
 import torch
 import torch.nn as nn
 
 from ... import ops
 from ...packing import pack_conv1x1, pack_geglu
-from ._base import half, PackedModule, f32, nchw_to_nhwc16, nhwc16_to_nchw, to_tokens, w16
+from ._base import PackedModule, f32, nchw_to_nhwc16, nhwc16_to_nchw, to_tokens, w16
 from .diffusionmodules.util import zero_module
 
 

@@ -16,10 +16,9 @@ exact in real arithmetic:
 """
 from __future__ import annotations
 
-import math
 import os
 from copy import deepcopy
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional
 
 import torch
 import torch.nn as nn

@@ -5,7 +5,6 @@ import math
 
 import numpy as np
 import torch
-import torch.nn as nn
 
 
 def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):

@@ -6,7 +6,7 @@ frozen weights broadcast ONCE at init over NCCL (NVLink 5 / NVSwitch), and no pe
 from __future__ import annotations
 
 import os
-from typing import List, Sequence
+from typing import List
 
 import torch
 import torch.distributed as dist

@@ -5,7 +5,7 @@ then moved to `device`.  Shared by bench.py, the tests and the oracle's golden s
 """
 from __future__ import annotations
 
-from typing import Dict, List, Tuple
+from typing import Dict, Tuple
 
 import torch
 
